@@ -1,0 +1,7 @@
+// TEST INFRASTRUCTURE — stand-in for glm/gtx/norm.hpp (see ../glm.hpp).
+#pragma once
+#include "../glm.hpp"
+
+namespace glm {
+inline float length2(const vec3 &v) { return dot(v, v); }
+} // namespace glm
