@@ -1,0 +1,216 @@
+/*
+ * sph_b200.h — C-ABI of the B200-native SPH simulation step.
+ *
+ * Drop-in scope: the SPHSystem::update() hot path of lijenicol/SPH-Fluid-Simulator, i.e. what sits
+ * behind
+ *     void updateParticles(Particle*, glm::mat4*, size_t, const SPHSettings&, float, bool onGPU)
+ *         (reference src/sph.h:19-22, src/sph.cpp:277-290)
+ * and its GPU leg
+ *     void updateParticlesGPU(Particle*, glm::mat4*, size_t, const SPHSettings&, float)
+ *         (reference src/kernels/sphGPU.h:8-11).
+ * Semantics are those of the reference's CPU step updateParticlesCPU (src/sph.cpp:195-275):
+ * same cell/hash function, same neighbour multisets (including the 16-bit hash-collision
+ * double count), same arithmetic order; see DESIGN.md.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (SPH_OK == 0) and never throws;
+ *   - a handle is single-owner: calls on one handle must be serialised by the caller;
+ *   - sph_step is asynchronous on the handle's internal stream; every call that returns data to
+ *     the host synchronises that stream first;
+ *   - "host" pointers are ordinary (pageable or pinned) host memory, "dev" pointers are device
+ *     memory on the handle's device;
+ *   - positions / velocities / forces are xyz-interleaved float triples unless stated otherwise.
+ *
+ * There is no CPU fallback: if no CUDA device is usable sph_create fails with SPH_ERR_CUDA.
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_B200_ABI_VERSION 1
+
+enum sph_status {
+    SPH_OK = 0,
+    SPH_ERR_INVALID = 1,  /* bad argument (null handle, n > capacity, ...) */
+    SPH_ERR_CUDA = 2,     /* a CUDA runtime call failed; see sph_last_error */
+    SPH_ERR_STATE = 3,    /* call not valid in the current state (e.g. step before upload) */
+    SPH_ERR_CAPACITY = 4  /* a caller-provided buffer or the handle's capacity is too small */
+};
+
+/* Replaces `struct SPHSettings`'s constructor inputs (reference src/SPHSystem.h:13-22) plus the
+ * constants the reference buries in code. */
+typedef struct sph_settings {
+    float mass;           /* SPHSettings::mass                         default 0.02  (src/Tester.cpp:90) */
+    float rest_density;   /* SPHSettings::restDensity                  default 1000 */
+    float gas_constant;   /* SPHSettings::gasConstant                  default 1 */
+    float viscosity;      /* SPHSettings::viscosity                    default 1.04 */
+    float h;              /* SPHSettings::h  (kernel radius = cell size) default 0.15 */
+    float g;              /* SPHSettings::g                            default -9.8 */
+    float tension;        /* SPHSettings::tension (unused by the step, as in the reference) 0.2 */
+    float dt;             /* fixed step of SPHSystem::update (src/SPHSystem.cpp:113)   0.003 */
+    float box_half_width; /* boxWidth  (src/sph.cpp:139)                               8 */
+    float elasticity;     /* elasticity (src/sph.cpp:140)                              0.5 */
+    float wall_offset;    /* the 0.0001f in the wall reflections (src/sph.cpp:154)     1e-4 */
+} sph_settings;
+
+/* Replaces the derived members SPHSettings' constructor computes (src/SPHSystem.cpp:19-25),
+ * evaluated on the host with the same float/double expression order. */
+typedef struct sph_derived {
+    float poly6, spiky_grad, spiky_lap, h2, self_dens, mass_poly6, sphere_scale;
+} sph_derived;
+
+/* Diagnostics of the most recent step (replaces nothing in the reference). */
+typedef struct sph_stats {
+    uint64_t count;           /* particles resident */
+    uint64_t steps;           /* steps taken since the last upload */
+    int32_t grid_origin[3];   /* cell coordinate of grid index (0,0,0) */
+    int32_t grid_dim[3];      /* cells per axis of the dense grid used by the last step */
+    uint64_t grid_cells;      /* product of grid_dim */
+    uint64_t clamped;         /* particles whose true cell fell outside the grid and were clamped */
+    uint64_t nan_count;       /* particles with a non-finite position component */
+    double mean_density;      /* mean of the last step's density */
+    double max_density;
+    double kinetic_energy;    /* 0.5 * mass * sum |v|^2 */
+} sph_stats;
+
+typedef struct sph_handle sph_handle;
+
+/* Order of the rows in a download. */
+enum sph_order {
+    SPH_ORDER_DEVICE = 0, /* the device's cell-sorted order of the last step */
+    SPH_ORDER_ID = 1,     /* row k holds the particle whose id is k (ids must be 0..n-1) */
+    SPH_ORDER_HASH16 = 2  /* stably sorted by start-of-step hash16: the order class the reference's
+                             std::sort leaves the array in (src/sph.cpp:184-192) */
+};
+
+/* ---- settings -------------------------------------------------------------------------- */
+
+/* The shipped defaults: SPHSettings(0.02,1000,1,1.04,0.15,-9.8,0.2) (src/Tester.cpp:90),
+ * dt 0.003 (src/SPHSystem.cpp:113), box 8 / elasticity 0.5 / offset 1e-4 (src/sph.cpp:139-154). */
+int sph_settings_default(sph_settings *out);
+
+/* SPHSettings::SPHSettings (src/SPHSystem.cpp:8-26). */
+int sph_settings_derive(const sph_settings *s, sph_derived *out);
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces the per-call allocations of updateParticlesGPU (src/kernels/sphGPU.cu:253-299) with
+ * persistent device state for up to `capacity` particles on CUDA device `device`. */
+int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle **out);
+int sph_destroy(sph_handle *h);
+
+/* Replace the settings of a live handle (GUI RESET semantics, src/Tester.cpp:169-173). */
+int sph_set_settings(sph_handle *h, const sph_settings *s);
+
+/* Human-readable description of the last failure on this handle (or of the last failed
+ * sph_create when h is NULL). Never NULL. */
+const char *sph_last_error(const sph_handle *h);
+
+/* ---- state in / out -------------------------------------------------------------------- */
+
+/* Load n particles (n <= capacity). id may be NULL (ids become 0..n-1). Replaces the H2D copy of
+ * src/kernels/sphGPU.cu:253-255. */
+int sph_upload(sph_handle *h, uint64_t n, const float *host_pos_xyz, const float *host_vel_xyz,
+               const uint32_t *host_id);
+/* Same, from device memory holding float4 rows (xyz + ignored w); ids 0..n-1. */
+int sph_upload_device(sph_handle *h, uint64_t n, const void *dev_pos_xyzw, const void *dev_vel_xyzw);
+
+/* Copy out whatever is non-NULL. pos/vel are the current state; force, density, pressure and
+ * hash16 are the values the last step computed (start-of-step hash, as Particle::hash holds
+ * after updateParticlesCPU). Replaces the D2H copies of src/kernels/sphGPU.cu:304-307. */
+int sph_download(sph_handle *h, int order, float *host_pos_xyz, float *host_vel_xyz,
+                 float *host_force_xyz, float *host_density, float *host_pressure,
+                 uint16_t *host_hash16, uint32_t *host_id);
+
+/* Renderer read-out (what SPHSystem::draw consumes, src/SPHSystem.cpp:119-134), device order.
+ * sph_read_positions: n rows of float4 (x, y, z, 1).
+ * sph_write_transforms: n column-major 4x4 matrices translate(pos) * scale(h/2)
+ *                       (src/sph.cpp:178-179). Destination is HOST memory. */
+int sph_read_positions(sph_handle *h, float *host_xyzw);
+int sph_write_transforms(sph_handle *h, float *host_mat4);
+/* Device-to-device variants for callers that own a mapped/interop buffer on the same device. */
+int sph_read_positions_device(sph_handle *h, void *dev_xyzw);
+int sph_write_transforms_device(sph_handle *h, void *dev_mat4);
+
+uint64_t sph_count(const sph_handle *h);
+uint64_t sph_capacity(const sph_handle *h);
+
+/* ---- the step -------------------------------------------------------------------------- */
+
+/* nsteps steps of updateParticlesCPU semantics with time step dt (src/sph.cpp:195-275). dt <= 0
+ * means "use settings.dt", which is what SPHSystem::update does (src/SPHSystem.cpp:113). */
+int sph_step(sph_handle *h, float dt, int nsteps);
+int sph_sync(sph_handle *h);
+
+/* Stateless form with the exact data contract of updateParticlesGPU
+ * (src/kernels/sphGPU.h:8-11): `host_particles` is an array of n 60-byte reference Particle
+ * records (src/Particle.h:4-10: position, velocity, acceleration, force, density, pressure,
+ * uint16 hash, 2 bytes padding), updated in place and returned sorted by start-of-step hash16;
+ * `host_mat4` (may be NULL) receives n column-major transforms in the same order. The
+ * `acceleration` field is carried through untouched. */
+int sph_update_particles_aos(sph_handle *h, void *host_particles, float *host_mat4, uint64_t n, float dt);
+
+/* ---- parity / diagnostics -------------------------------------------------------------- */
+
+/* The hash16 -> first-index table of createNeighborTable (src/neighborTable.cpp:19-37) for the
+ * last step's start-of-step hashes: 262144 entries, 0xFFFFFFFF where empty. */
+int sph_hash_table(sph_handle *h, uint32_t *host_table);
+
+/* Neighbour multisets of the CURRENT positions, enumerated by the same traversal code the
+ * density / force kernels use. counts[k] (device order) = accepted entries of row k with
+ * multiplicity; if list != NULL it receives, for row k, the ids of its neighbours at
+ * [offsets[k], offsets[k+1]) where offsets is the exclusive prefix sum of counts (n+1 entries,
+ * filled by this call); list_capacity is in entries. ids_out (optional) = id of each row. */
+int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offsets,
+                       uint32_t *host_list, uint64_t list_capacity, uint32_t *host_ids_out);
+
+int sph_get_stats(sph_handle *h, sph_stats *out);
+
+/* Per-pass device times in milliseconds for the most recent sph_step call's LAST step, measured
+ * with CUDA events when enabled (replaces the Timer blocks of src/sph.cpp:235,249,262).
+ * Order: grid build (hash+sort+ranges), density, forces, integrate. */
+int sph_enable_pass_timing(sph_handle *h, int enable);
+int sph_pass_times(sph_handle *h, float *ms4);
+
+/* Raw CUDA stream of the handle (cudaStream_t as void*), so a caller can order its own work or
+ * record events on it. */
+void *sph_stream(sph_handle *h);
+
+
+/* ---- scenes and the SPHSystem class surface ------------------------------------------- */
+
+/* initParticles (src/SPHSystem.cpp:76-108): width^3 lattice, spacing h + 0.01, origin
+ * (-1.5, h + 0.1, -1.5), glibc srand(1024)/rand() jitter, zero velocity; row index
+ * i + (j + width*k)*width. Host arrays of 3*width^3 floats. */
+int sph_scene_cube(int width, float h, float *host_pos_xyz, float *host_vel_xyz);
+/* The same generator for an nx*ny*nz block (dam-break scenes). */
+int sph_scene_block(int nx, int ny, int nz, float sep, float x0, float y0, float z0, float h, unsigned seed,
+                    float *host_pos_xyz, float *host_vel_xyz);
+
+/* class SPHSystem (src/SPHSystem.h:24-57) for hosts that cannot include the C++ header
+ * (sph-fluid-simulator_b200/host/SPHSystem.h): constructor, update, reset, startSimulation,
+ * particleCount, and the renderer read-out that replaces `particles` / `sphereModelMtxs`.
+ * run_on_gpu = 0 fails: there is no CPU step. */
+typedef struct sph_system sph_system;
+int sph_system_create(int cube_width, const sph_settings *s, int run_on_gpu, int device, sph_system **out);
+int sph_system_destroy(sph_system *sys);
+const char *sph_system_last_error(const sph_system *sys);
+int sph_system_start(sph_system *sys);             /* SPHSystem::startSimulation */
+int sph_system_update(sph_system *sys, float dt);  /* SPHSystem::update (no-op until started; dt := 0.003) */
+int sph_system_reset(sph_system *sys);             /* SPHSystem::reset */
+uint64_t sph_system_count(const sph_system *sys);  /* SPHSystem::particleCount */
+sph_handle *sph_system_handle(sph_system *sys);
+int sph_system_positions(sph_system *sys, float *host_xyzw);        /* count rows of (x,y,z,1) */
+int sph_system_model_matrices(sph_system *sys, float *host_mat4);   /* count column-major mat4 */
+int sph_system_download(sph_system *sys, float *host_pos_xyz, float *host_vel_xyz); /* by particle id */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPH_B200_H */

@@ -204,7 +204,7 @@ class Reference:
         L.ref_get_cell.argtypes = [C.c_float] * 4 + [ip]
         L.ref_neighbor_table.argtypes = [C.c_uint64, u16p, u32p]
         L.ref_init_cube.argtypes = [C.c_int, fp, fp, fp, fp]
-        L.ref_class_run.argtypes = [C.c_int, fp, C.c_int, C.c_int, C.c_int, fp, fp]
+        L.ref_class_run.argtypes = [C.c_int, fp, C.c_int, C.c_int, C.c_int, fp, fp, u32p]
         L.ref_step.argtypes = [C.c_uint64, fp, C.c_float, C.c_int, C.c_int, fp, fp, u32p, fp, fp, fp, u16p, fp]
         L.ref_time_steps.argtypes = [C.c_uint64, fp, C.c_float, C.c_int, C.c_int, fp, fp]
         L.ref_time_steps.restype = C.c_double
@@ -249,9 +249,10 @@ class Reference:
         n = width ** 3
         pos = np.empty((n, 3), np.float32)
         vel = np.empty((n, 3), np.float32)
+        ids = np.empty(n, np.uint32)
         self.lib.ref_class_run(width, self._s7(s7), nsteps, int(start), int(reset_after),
-                               _p(pos, C.c_float), _p(vel, C.c_float))
-        return pos, vel
+                               _p(pos, C.c_float), _p(vel, C.c_float), _p(ids, C.c_uint32))
+        return pos, vel, ids
 
     def step(self, s7, dt, pos, vel, ids=None, nsteps=1, on_gpu=False, transforms=False):
         pos = _f32(pos).copy()

@@ -148,14 +148,16 @@ void ref_init_cube(int width, const float *s7, float *pos, float *vel, float *tr
 // (src/Tester.cpp:110-125, 210-221): returns positions after `nsteps` update() calls.
 // started_first = 0 checks that update() is a no-op until startSimulation().
 void ref_class_run(int width, const float *s7, int nsteps, int start, int reset_after, float *pos,
-                   float *vel)
+                   float *vel, uint32_t *id)
 {
     QuietStreams q;
     SPHSystem *sys = new SPHSystem((size_t)width, make(s7), false);
+    for (uint32_t i = 0; i < sys->particleCount; ++i)  // ids ride in the dead acceleration field
+        std::memcpy(&sys->particles[i].acceleration.x, &i, 4);
     if (start) sys->startSimulation();
     for (int i = 0; i < nsteps; ++i) sys->update(0.016f);
     if (reset_after) sys->reset();
-    unpack(sys->particleCount, sys->particles, pos, vel, nullptr, nullptr, nullptr, nullptr, nullptr);
+    unpack(sys->particleCount, sys->particles, pos, vel, id, nullptr, nullptr, nullptr, nullptr);
 }
 
 // nsteps calls of updateParticles(..., onGPU) (src/sph.cpp:277-290) from the given state.

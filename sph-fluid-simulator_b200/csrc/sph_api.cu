@@ -1,0 +1,772 @@
+// C-ABI implementation (include/sph_b200.h): persistent device state, the step pipeline and the
+// host<->device boundary. One translation unit: the kernels live in the .cuh files next to it.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared ...
+// (--fmad=false is part of the parity contract, see sph_device.cuh).
+#include "../../include/sph_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "sph_device.cuh"
+#include "sph_grid.cuh"
+#include "sph_physics.cuh"
+#include "sph_io.cuh"
+
+using namespace sphb;
+
+namespace {
+
+thread_local char g_create_error[512] = "";
+
+constexpr float REF_PI = 3.14159265f;  // src/SPHSystem.cpp:6
+
+struct PassEvents {
+    cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+}  // namespace
+
+struct sph_handle {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    uint64_t cap = 0, n = 0, steps = 0;
+    sph_settings settings{};
+    sph_derived derived{};
+    Params P{};
+
+    float4 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr};
+    int cur = 0;
+    float4 *force = nullptr;
+    float *rho = nullptr;
+    uint2 *cell_rank = nullptr;
+    uint32_t *slot_src = nullptr, *order = nullptr, *map = nullptr;
+    uint32_t *cells = nullptr;
+    uint32_t max_cells = 0;
+    uint32_t *h16_cells = nullptr;  // 65536 + 2 counters for the hash16 ordering
+    uint32_t *const_65536 = nullptr;
+    unsigned long long *tile_state = nullptr;
+    GridDesc *gd = nullptr;
+    StepCounters *ctr = nullptr;
+    StatsAccum *stats_acc = nullptr;
+    uint32_t epoch = 0;
+    int parity = 0;
+    bool have_state = false;  // particles uploaded
+    bool have_step = false;   // force / density / hash16 rows are valid and aligned with pos / vel
+
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    bool timing = false;
+    PassEvents ev;
+    float pass_ms[4] = {0, 0, 0, 0};
+    bool pass_valid = false;
+
+    char err[512] = "";
+};
+
+namespace {
+
+int fail(sph_handle *h, int code, const char *fmt, ...)
+{
+    char *dst = h ? h->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, SPH_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,      \
+                        cudaGetErrorString(e_));                                                   \
+    } while (0)
+#define CK_LAUNCH() CK(cudaGetLastError())
+
+inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// SPHSettings::SPHSettings, src/SPHSystem.cpp:8-26. `pow(h, 9)` with a float and an int is the
+// double pow; the float*float products are formed first and the quotient is rounded once when
+// stored to the float member.
+void derive(const sph_settings &s, sph_derived &d)
+{
+    const float h = s.h;
+    d.poly6 = (float)((double)315.0f / ((double)(64.0f * REF_PI) * std::pow((double)h, 9.0)));
+    d.spiky_grad = (float)((double)-45.0f / ((double)REF_PI * std::pow((double)h, 6.0)));
+    d.spiky_lap = (float)((double)45.0f / ((double)REF_PI * std::pow((double)h, 6.0)));
+    d.h2 = h * h;
+    d.self_dens = (float)((double)(s.mass * d.poly6) * std::pow((double)h, 6.0));
+    d.mass_poly6 = s.mass * d.poly6;
+    d.sphere_scale = h / 2.f;
+}
+
+void make_params(const sph_settings &s, const sph_derived &d, Params &P)
+{
+    P.h = s.h;
+    P.h2 = d.h2;
+    P.mass = s.mass;
+    P.mass_poly6 = s.mass * d.poly6;  // recomputed as src/sph.cpp:33 does
+    P.self_dens = d.self_dens;
+    P.gas_constant = s.gas_constant;
+    P.rest_density = s.rest_density;
+    P.visc_mass = s.viscosity * s.mass;
+    P.spiky_grad = d.spiky_grad;
+    P.spiky_lap = d.spiky_lap;
+    P.g = s.g;
+    P.h_minus_box = s.h - s.box_half_width;
+    P.box_minus_h = -s.h + s.box_half_width;
+    P.two_h = 2 * s.h;
+    P.two_hmb = 2 * (s.h - s.box_half_width);
+    P.two_nhmb = 2 * -(s.h - s.box_half_width);
+    P.wall_offset = s.wall_offset;
+    P.elasticity = s.elasticity;
+    P.sphere_scale = d.sphere_scale;
+}
+
+int validate_settings(sph_handle *h, const sph_settings *s)
+{
+    if (!s) return fail(h, SPH_ERR_INVALID, "settings is NULL");
+    if (!(s->h > 0.f) || !std::isfinite(s->h)) return fail(h, SPH_ERR_INVALID, "settings.h must be a positive finite number");
+    return SPH_OK;
+}
+
+int ensure_scratch(sph_handle *h, size_t bytes)
+{
+    if (bytes <= h->scratch_bytes) return SPH_OK;
+    if (h->scratch) CK(cudaFree(h->scratch));
+    h->scratch = nullptr;
+    h->scratch_bytes = 0;
+    CK(cudaMalloc(&h->scratch, bytes));
+    h->scratch_bytes = bytes;
+    return SPH_OK;
+}
+
+int enter(sph_handle *h)
+{
+    if (!h) return fail(nullptr, SPH_ERR_INVALID, "handle is NULL");
+    CK(cudaSetDevice(h->device));
+    return SPH_OK;
+}
+
+// bbox of the current positions into bbox[parity] (after an upload; in steady state the
+// integration kernel has already produced it).
+int compute_bbox(sph_handle *h)
+{
+    k_reset_bbox<<<1, 32, 0, h->stream>>>(h->ctr, h->parity);
+    CK_LAUNCH();
+    if (h->n) {
+        k_bbox<<<blocks_for(h->n, GRID_THREADS), GRID_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)h->n, h->P.h,
+                                                                            h->ctr, h->parity);
+        CK_LAUNCH();
+    }
+    return SPH_OK;
+}
+
+// Neighbour-search build for the current positions: plan -> zero -> histogram -> scan -> place
+// -> stable order -> gather. Flips pos/vel buffers; afterwards rows are in cell order and
+// h->cells holds the cell start offsets.
+int build_grid(sph_handle *h)
+{
+    const uint32_t n = (uint32_t)h->n;
+    cudaStream_t s = h->stream;
+    k_plan<<<1, 32, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells);
+    CK_LAUNCH();
+    k_zero_cells<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->cells, h->gd);
+    CK_LAUNCH();
+    k_cell_hist<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->pos[h->cur], n, h->P.h, h->gd, h->cells,
+                                                                   h->cell_rank, h->ctr);
+    CK_LAUNCH();
+    ++h->epoch;
+    k_scan_exclusive<<<h->num_sms * 4, SCAN_THREADS, 0, s>>>(h->cells, &h->gd->ncells, h->tile_state,
+                                                            &h->ctr->ticket, h->epoch);
+    CK_LAUNCH();
+    k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, n, h->cells, h->slot_src);
+    CK_LAUNCH();
+    k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot_src, h->cell_rank, n, h->cells,
+                                                                      h->order);
+    CK_LAUNCH();
+    k_gather_sorted<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->order, n, h->P.h, h->pos[h->cur],
+                                                                       h->vel[h->cur], h->pos[h->cur ^ 1],
+                                                                       h->vel[h->cur ^ 1]);
+    CK_LAUNCH();
+    h->cur ^= 1;
+    return SPH_OK;
+}
+
+int step_once(sph_handle *h, float dt, bool timed)
+{
+    const uint32_t n = (uint32_t)h->n;
+    cudaStream_t s = h->stream;
+    if (timed) CK(cudaEventRecord(h->ev.e[0], s));
+    int rc = build_grid(h);
+    if (rc) return rc;
+    if (timed) CK(cudaEventRecord(h->ev.e[1], s));
+    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->rho);
+    CK_LAUNCH();
+    if (timed) CK(cudaEventRecord(h->ev.e[2], s));
+    k_forces<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->rho, n, h->gd,
+                                                                h->cells, h->P, h->force);
+    CK_LAUNCH();
+    if (timed) CK(cudaEventRecord(h->ev.e[3], s));
+    k_integrate<<<blocks_for(n, 256), 256, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho, n, h->P, dt,
+                                                  h->ctr, h->parity ^ 1);
+    CK_LAUNCH();
+    if (timed) CK(cudaEventRecord(h->ev.e[4], s));
+    h->parity ^= 1;
+    ++h->steps;
+    h->have_step = true;
+    return SPH_OK;
+}
+
+// map[d] = device row that lands at row d when rows are stably sorted by start-of-step hash16.
+// Leaves the bucket start offsets (65537 entries) in h->h16_cells.
+int build_hash16_order(sph_handle *h, bool need_map)
+{
+    const uint32_t n = (uint32_t)h->n;
+    cudaStream_t s = h->stream;
+    CK(cudaMemsetAsync(h->h16_cells, 0, sizeof(uint32_t) * 65540, s));
+    CK(cudaMemsetAsync(&h->ctr->aux[0], 0, sizeof(uint32_t), s));
+    if (n) {
+        k_hash16_hist<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->pos[h->cur], n, h->h16_cells,
+                                                                     need_map ? h->cell_rank : nullptr);
+        CK_LAUNCH();
+    }
+    ++h->epoch;
+    k_scan_exclusive<<<32, SCAN_THREADS, 0, s>>>(h->h16_cells, h->const_65536, h->tile_state, &h->ctr->aux[0],
+                                                h->epoch);
+    CK_LAUNCH();
+    if (need_map && n) {
+        k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, n, h->h16_cells, h->slot_src);
+        CK_LAUNCH();
+        k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot_src, h->cell_rank, n,
+                                                                          h->h16_cells, h->map);
+        CK_LAUNCH();
+    }
+    return SPH_OK;
+}
+
+int after_upload(sph_handle *h, uint64_t n)
+{
+    h->n = n;
+    h->steps = 0;
+    h->have_state = true;
+    h->have_step = false;
+    h->pass_valid = false;
+    return compute_bbox(h);
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int sph_settings_default(sph_settings *out)
+{
+    if (!out) return SPH_ERR_INVALID;
+    out->mass = 0.02f;          // src/Tester.cpp:90
+    out->rest_density = 1000.f;
+    out->gas_constant = 1.f;
+    out->viscosity = 1.04f;
+    out->h = 0.15f;
+    out->g = -9.8f;
+    out->tension = 0.2f;
+    out->dt = 0.003f;           // src/SPHSystem.cpp:113
+    out->box_half_width = 8.f;  // src/sph.cpp:139
+    out->elasticity = 0.5f;     // src/sph.cpp:140
+    out->wall_offset = 0.0001f; // src/sph.cpp:154
+    return SPH_OK;
+}
+
+int sph_settings_derive(const sph_settings *s, sph_derived *out)
+{
+    if (!s || !out) return SPH_ERR_INVALID;
+    derive(*s, *out);
+    return SPH_OK;
+}
+
+const char *sph_last_error(const sph_handle *h) { return h ? h->err : g_create_error; }
+
+int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle **out)
+{
+    sph_handle *h = nullptr;  // errors before the handle exists go to the thread-local buffer
+    if (!out) return fail(h, SPH_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = validate_settings(h, s);
+    if (rc) return rc;
+    if (capacity == 0 || capacity > 0xfffffff0ull)
+        return fail(h, SPH_ERR_INVALID, "capacity must be in [1, 2^32-16], got %llu", (unsigned long long)capacity);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev)
+        return fail(h, SPH_ERR_INVALID, "device %d out of range (%d CUDA devices visible)", device, ndev);
+    CK(cudaSetDevice(device));
+
+    sph_handle *nh = new (std::nothrow) sph_handle();
+    if (!nh) return fail(h, SPH_ERR_INVALID, "out of host memory");
+    nh->device = device;
+    nh->cap = capacity;
+    nh->settings = *s;
+    derive(*s, nh->derived);
+    make_params(*s, nh->derived, nh->P);
+
+    // From here on errors are recorded in the new handle and copied out on failure.
+    h = nh;
+    auto bail = [&](int code) {
+        std::snprintf(g_create_error, sizeof g_create_error, "%s", nh->err);
+        sph_destroy(nh);
+        return code;
+    };
+#define CKC(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            fail(h, SPH_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,            \
+                 cudaGetErrorString(e_));                                                         \
+            return bail(SPH_ERR_CUDA);                                                            \
+        }                                                                                         \
+    } while (0)
+
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    nh->num_sms = prop.multiProcessorCount;
+    CKC(cudaStreamCreateWithFlags(&nh->stream, cudaStreamNonBlocking));
+
+    // Dense-grid allocation: 32 cells per particle of capacity, within [2^22, 2^30]
+    // (overridable for experiments with SPH_B200_MAX_CELLS).
+    uint64_t mc = capacity * 32ull;
+    if (mc < (1ull << 22)) mc = 1ull << 22;
+    if (mc > (1ull << 30)) mc = 1ull << 30;
+    if (const char *e = std::getenv("SPH_B200_MAX_CELLS")) {
+        const unsigned long long v = std::strtoull(e, nullptr, 10);
+        if (v >= 27 && v <= (1ull << 31)) mc = v;
+    }
+    nh->max_cells = (uint32_t)mc;
+
+    const size_t cap = (size_t)capacity;
+    for (int b = 0; b < 2; ++b) {
+        CKC(cudaMalloc(&nh->pos[b], sizeof(float4) * cap));
+        CKC(cudaMalloc(&nh->vel[b], sizeof(float4) * cap));
+    }
+    CKC(cudaMalloc(&nh->force, sizeof(float4) * cap));
+    CKC(cudaMalloc(&nh->rho, sizeof(float) * cap));
+    CKC(cudaMalloc(&nh->cell_rank, sizeof(uint2) * cap));
+    CKC(cudaMalloc(&nh->slot_src, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->order, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->map, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->cells, sizeof(uint32_t) * ((size_t)nh->max_cells + 8)));
+    CKC(cudaMalloc(&nh->h16_cells, sizeof(uint32_t) * 65540));
+    CKC(cudaMalloc(&nh->const_65536, sizeof(uint32_t)));
+    const size_t ntile = ((size_t)nh->max_cells + 1 + SCAN_TILE - 1) / SCAN_TILE + 1;
+    CKC(cudaMalloc(&nh->tile_state, sizeof(unsigned long long) * ntile));
+    CKC(cudaMemsetAsync(nh->tile_state, 0, sizeof(unsigned long long) * ntile, nh->stream));
+    CKC(cudaMalloc(&nh->gd, sizeof(GridDesc)));
+    CKC(cudaMalloc(&nh->ctr, sizeof(StepCounters)));
+    CKC(cudaMemsetAsync(nh->ctr, 0, sizeof(StepCounters), nh->stream));
+    CKC(cudaMemsetAsync(nh->gd, 0, sizeof(GridDesc), nh->stream));
+    CKC(cudaMalloc(&nh->stats_acc, sizeof(StatsAccum)));
+    const uint32_t c65536 = 65536u;
+    CKC(cudaMemcpyAsync(nh->const_65536, &c65536, sizeof c65536, cudaMemcpyHostToDevice, nh->stream));
+    for (auto &e : nh->ev.e) CKC(cudaEventCreate(&e));
+    CKC(cudaStreamSynchronize(nh->stream));
+#undef CKC
+    *out = nh;
+    return SPH_OK;
+}
+
+int sph_destroy(sph_handle *h)
+{
+    if (!h) return SPH_ERR_INVALID;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int b = 0; b < 2; ++b) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); }
+    cudaFree(h->force); cudaFree(h->rho); cudaFree(h->cell_rank); cudaFree(h->slot_src);
+    cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
+    cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
+    cudaFree(h->stats_acc); cudaFree(h->scratch);
+    for (auto &e : h->ev.e) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SPH_OK;
+}
+
+int sph_set_settings(sph_handle *h, const sph_settings *s)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    rc = validate_settings(h, s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    h->settings = *s;
+    derive(*s, h->derived);
+    make_params(*s, h->derived, h->P);
+    h->have_step = false;
+    if (h->have_state) return compute_bbox(h);  // cells depend on h
+    return SPH_OK;
+}
+
+uint64_t sph_count(const sph_handle *h) { return h ? h->n : 0; }
+uint64_t sph_capacity(const sph_handle *h) { return h ? h->cap : 0; }
+void *sph_stream(sph_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+// ---- state in / out ---------------------------------------------------------------------------
+
+int sph_upload(sph_handle *h, uint64_t n, const float *host_pos, const float *host_vel, const uint32_t *host_id)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "upload of %llu particles exceeds capacity %llu",
+                                (unsigned long long)n, (unsigned long long)h->cap);
+    if (n && (!host_pos || !host_vel)) return fail(h, SPH_ERR_INVALID, "pos/vel is NULL");
+    const size_t b3 = align_up(sizeof(float) * 3 * n, 256), b1 = align_up(sizeof(uint32_t) * n, 256);
+    rc = ensure_scratch(h, 2 * b3 + b1 + 256);
+    if (rc) return rc;
+    char *sc = (char *)h->scratch;
+    float *dpos = (float *)sc, *dvel = (float *)(sc + b3);
+    uint32_t *did = (uint32_t *)(sc + 2 * b3);
+    if (n) {
+        CK(cudaMemcpyAsync(dpos, host_pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(dvel, host_vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+        if (host_id) CK(cudaMemcpyAsync(did, host_id, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, h->stream));
+        k_import_xyz<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(dpos, dvel, host_id ? did : nullptr,
+                                                                            (uint32_t)n, h->pos[h->cur], h->vel[h->cur]);
+        CK_LAUNCH();
+    }
+    rc = after_upload(h, n);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffers
+    return SPH_OK;
+}
+
+int sph_upload_device(sph_handle *h, uint64_t n, const void *dev_pos, const void *dev_vel)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "upload of %llu particles exceeds capacity %llu",
+                                (unsigned long long)n, (unsigned long long)h->cap);
+    if (n && (!dev_pos || !dev_vel)) return fail(h, SPH_ERR_INVALID, "pos/vel is NULL");
+    if (n) {
+        k_import_xyzw<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>((const float4 *)dev_pos, (const float4 *)dev_vel,
+                                                                             (uint32_t)n, h->pos[h->cur], h->vel[h->cur]);
+        CK_LAUNCH();
+    }
+    rc = after_upload(h, n);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_download(sph_handle *h, int order, float *host_pos, float *host_vel, float *host_force, float *host_density,
+                 float *host_pressure, uint16_t *host_hash16, uint32_t *host_id)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if ((host_force || host_density || host_pressure || host_hash16 || order == SPH_ORDER_HASH16) && !h->have_step)
+        return fail(h, SPH_ERR_STATE, "force/density/pressure/hash16 are only defined after a step");
+    if (order != SPH_ORDER_DEVICE && order != SPH_ORDER_ID && order != SPH_ORDER_HASH16)
+        return fail(h, SPH_ERR_INVALID, "unknown order %d", order);
+    const uint64_t n = h->n;
+    if (n == 0) return SPH_OK;
+    const size_t b3 = align_up(sizeof(float) * 3 * n, 256), b1 = align_up(sizeof(float) * n, 256);
+    rc = ensure_scratch(h, 3 * b3 + 4 * b1 + 256);
+    if (rc) return rc;
+    char *sc = (char *)h->scratch;
+    ExportPtrs out{};
+    out.pos3 = host_pos ? (float *)sc : nullptr;
+    out.vel3 = host_vel ? (float *)(sc + b3) : nullptr;
+    out.force3 = host_force ? (float *)(sc + 2 * b3) : nullptr;
+    out.density = host_density ? (float *)(sc + 3 * b3) : nullptr;
+    out.pressure = host_pressure ? (float *)(sc + 3 * b3 + b1) : nullptr;
+    out.id = host_id ? (uint32_t *)(sc + 3 * b3 + 2 * b1) : nullptr;
+    out.hash16 = host_hash16 ? (uint16_t *)(sc + 3 * b3 + 3 * b1) : nullptr;
+
+    const uint32_t *map = nullptr;
+    if (order == SPH_ORDER_ID) {
+        CK(cudaMemsetAsync(&h->ctr->aux[1], 0, sizeof(uint32_t), h->stream));
+        k_rows_by_id<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->vel[h->cur], (uint32_t)n, h->map,
+                                                                            &h->ctr->aux[1]);
+        CK_LAUNCH();
+        uint32_t bad = 0;
+        CK(cudaMemcpyAsync(&bad, &h->ctr->aux[1], sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (bad) return fail(h, SPH_ERR_STATE, "SPH_ORDER_ID needs ids in [0, n): %u rows are out of range", bad);
+        map = h->map;
+    } else if (order == SPH_ORDER_HASH16) {
+        rc = build_hash16_order(h, true);
+        if (rc) return rc;
+        map = h->map;
+    }
+    k_export<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho,
+                                                                    (uint32_t)n, map, h->P, out);
+    CK_LAUNCH();
+    if (host_pos) CK(cudaMemcpyAsync(host_pos, out.pos3, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (host_vel) CK(cudaMemcpyAsync(host_vel, out.vel3, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (host_force) CK(cudaMemcpyAsync(host_force, out.force3, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (host_density) CK(cudaMemcpyAsync(host_density, out.density, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (host_pressure) CK(cudaMemcpyAsync(host_pressure, out.pressure, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (host_id) CK(cudaMemcpyAsync(host_id, out.id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (host_hash16) CK(cudaMemcpyAsync(host_hash16, out.hash16, sizeof(uint16_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_read_positions_device(sph_handle *h, void *dev_xyzw)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!dev_xyzw) return fail(h, SPH_ERR_INVALID, "destination is NULL");
+    if (h->n) {
+        k_positions_xyz1<<<blocks_for(h->n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)h->n,
+                                                                                   (float4 *)dev_xyzw);
+        CK_LAUNCH();
+    }
+    return SPH_OK;
+}
+
+int sph_read_positions(sph_handle *h, float *host_xyzw)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!host_xyzw) return fail(h, SPH_ERR_INVALID, "destination is NULL");
+    rc = ensure_scratch(h, sizeof(float4) * h->n + 256);
+    if (rc) return rc;
+    rc = sph_read_positions_device(h, h->scratch);
+    if (rc) return rc;
+    if (h->n) CK(cudaMemcpyAsync(host_xyzw, h->scratch, sizeof(float4) * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_write_transforms_device(sph_handle *h, void *dev_mat4)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!dev_mat4) return fail(h, SPH_ERR_INVALID, "destination is NULL");
+    if (h->n) {
+        k_transforms<<<blocks_for(h->n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)h->n, nullptr,
+                                                                               h->P.sphere_scale, (float4 *)dev_mat4);
+        CK_LAUNCH();
+    }
+    return SPH_OK;
+}
+
+int sph_write_transforms(sph_handle *h, float *host_mat4)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!host_mat4) return fail(h, SPH_ERR_INVALID, "destination is NULL");
+    rc = ensure_scratch(h, 64 * h->n + 256);
+    if (rc) return rc;
+    rc = sph_write_transforms_device(h, h->scratch);
+    if (rc) return rc;
+    if (h->n) CK(cudaMemcpyAsync(host_mat4, h->scratch, 64 * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+// ---- the step ---------------------------------------------------------------------------------
+
+int sph_step(sph_handle *h, float dt, int nsteps)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "sph_step before sph_upload");
+    if (nsteps < 0) return fail(h, SPH_ERR_INVALID, "nsteps must be >= 0");
+    if (!(dt > 0.f)) dt = h->settings.dt;  // SPHSystem::update's fixed step (src/SPHSystem.cpp:113)
+    if (h->n == 0) return SPH_OK;
+    for (int k = 0; k < nsteps; ++k) {
+        const bool timed = h->timing && k == nsteps - 1;
+        rc = step_once(h, dt, timed);
+        if (rc) return rc;
+        if (timed) h->pass_valid = true;
+    }
+    return SPH_OK;
+}
+
+int sph_sync(sph_handle *h)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_update_particles_aos(sph_handle *h, void *host_particles, float *host_mat4, uint64_t n, float dt)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "%llu particles exceed capacity %llu", (unsigned long long)n,
+                                (unsigned long long)h->cap);
+    if (n && !host_particles) return fail(h, SPH_ERR_INVALID, "particles is NULL");
+    if (!(dt > 0.f)) dt = h->settings.dt;
+    if (n == 0) { h->n = 0; h->have_state = true; h->have_step = false; return SPH_OK; }
+    const size_t ba = align_up((size_t)60 * n, 256), bm = align_up((size_t)64 * n, 256);
+    rc = ensure_scratch(h, 2 * ba + bm + 256);
+    if (rc) return rc;
+    char *sc = (char *)h->scratch;
+    uint32_t *aos_in = (uint32_t *)sc, *aos_out = (uint32_t *)(sc + ba);
+    float4 *mats = (float4 *)(sc + 2 * ba);
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(aos_in, host_particles, (size_t)60 * n, cudaMemcpyHostToDevice, s));
+    k_import_aos<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(aos_in, (uint32_t)n, h->pos[h->cur], h->vel[h->cur]);
+    CK_LAUNCH();
+    rc = after_upload(h, n);
+    if (rc) return rc;
+    rc = step_once(h, dt, false);
+    if (rc) return rc;
+    rc = build_hash16_order(h, true);
+    if (rc) return rc;
+    k_export_aos<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho,
+                                                                (uint32_t)n, h->map, h->P, aos_in, aos_out);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(host_particles, aos_out, (size_t)60 * n, cudaMemcpyDeviceToHost, s));
+    if (host_mat4) {
+        k_transforms<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->pos[h->cur], (uint32_t)n, h->map,
+                                                                    h->P.sphere_scale, mats);
+        CK_LAUNCH();
+        CK(cudaMemcpyAsync(host_mat4, mats, (size_t)64 * n, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return SPH_OK;
+}
+
+// ---- parity / diagnostics ---------------------------------------------------------------------
+
+int sph_hash_table(sph_handle *h, uint32_t *host_table)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_step) return fail(h, SPH_ERR_STATE, "the hash table is only defined after a step");
+    if (!host_table) return fail(h, SPH_ERR_INVALID, "destination is NULL");
+    rc = build_hash16_order(h, false);
+    if (rc) return rc;
+    rc = ensure_scratch(h, sizeof(uint32_t) * REF_TABLE_SIZE);
+    if (rc) return rc;
+    k_ref_table<<<blocks_for(REF_TABLE_SIZE, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->h16_cells, (uint32_t *)h->scratch);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(host_table, h->scratch, sizeof(uint32_t) * REF_TABLE_SIZE, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offsets, uint32_t *host_list,
+                       uint64_t list_capacity, uint32_t *host_ids_out)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!host_counts) return fail(h, SPH_ERR_INVALID, "counts is NULL");
+    if (host_list && !host_offsets) return fail(h, SPH_ERR_INVALID, "offsets is required with list");
+    const uint64_t n = h->n;
+    if (n == 0) { if (host_offsets) host_offsets[0] = 0; return SPH_OK; }
+    // Rebuild the grid for the current positions. Rows get re-sorted, so the previous step's
+    // force/density rows no longer line up with pos/vel.
+    h->have_step = false;
+    rc = build_grid(h);
+    if (rc) return rc;
+    uint32_t *dcounts = h->slot_src;  // free after build_grid
+    k_neighbor_lists<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)n,
+                                                                                h->gd, h->cells, h->P, dcounts, nullptr, nullptr);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(host_counts, dcounts, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (host_ids_out) {
+        rc = ensure_scratch(h, sizeof(uint32_t) * n + 256);
+        if (rc) return rc;
+        ExportPtrs out{};
+        out.id = (uint32_t *)h->scratch;
+        k_export<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho,
+                                                                        (uint32_t)n, nullptr, h->P, out);
+        CK_LAUNCH();
+        CK(cudaMemcpyAsync(host_ids_out, out.id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (!host_offsets) return SPH_OK;
+    uint64_t total = 0;
+    for (uint64_t i = 0; i < n; ++i) { host_offsets[i] = total; total += host_counts[i]; }
+    host_offsets[n] = total;
+    if (!host_list) return SPH_OK;
+    if (total > list_capacity)
+        return fail(h, SPH_ERR_CAPACITY, "neighbour list needs %llu entries, capacity is %llu",
+                    (unsigned long long)total, (unsigned long long)list_capacity);
+    if (total == 0) return SPH_OK;
+    const size_t bo = align_up(sizeof(uint64_t) * (n + 1), 256);
+    rc = ensure_scratch(h, bo + sizeof(uint32_t) * total + 256);
+    if (rc) return rc;
+    unsigned long long *doff = (unsigned long long *)h->scratch;
+    uint32_t *dlist = (uint32_t *)((char *)h->scratch + bo);
+    CK(cudaMemcpyAsync(doff, host_offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
+    k_neighbor_lists<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)n,
+                                                                                h->gd, h->cells, h->P, dcounts, doff, dlist);
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(host_list, dlist, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+int sph_get_stats(sph_handle *h, sph_stats *out)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!out) return fail(h, SPH_ERR_INVALID, "out is NULL");
+    std::memset(out, 0, sizeof *out);
+    out->count = h->n;
+    out->steps = h->steps;
+    if (!h->have_state || h->n == 0) return SPH_OK;
+    GridDesc g{};
+    StepCounters c{};
+    StatsAccum a{};
+    CK(cudaMemsetAsync(h->stats_acc, 0, sizeof(StatsAccum), h->stream));
+    if (h->have_step) {
+        k_stats<<<h->num_sms * 4, IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->rho, (uint32_t)h->n, h->stats_acc);
+        CK_LAUNCH();
+    }
+    CK(cudaMemcpyAsync(&a, h->stats_acc, sizeof a, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&g, h->gd, sizeof g, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&c, h->ctr, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    out->grid_origin[0] = g.ox; out->grid_origin[1] = g.oy; out->grid_origin[2] = g.oz;
+    out->grid_dim[0] = g.nx; out->grid_dim[1] = g.ny; out->grid_dim[2] = g.nz;
+    out->grid_cells = g.ncells;
+    out->clamped = c.clamped;
+    out->nan_count = a.nan_count;
+    out->mean_density = a.sum_rho / (double)h->n;
+    float mx;
+    std::memcpy(&mx, &a.max_rho_bits, 4);
+    out->max_density = mx;
+    out->kinetic_energy = 0.5 * (double)h->settings.mass * a.sum_v2;
+    return SPH_OK;
+}
+
+int sph_enable_pass_timing(sph_handle *h, int enable)
+{
+    if (!h) return SPH_ERR_INVALID;
+    h->timing = enable != 0;
+    h->pass_valid = false;
+    return SPH_OK;
+}
+
+int sph_pass_times(sph_handle *h, float *ms4)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!ms4) return fail(h, SPH_ERR_INVALID, "destination is NULL");
+    if (!h->pass_valid) return fail(h, SPH_ERR_STATE, "no timed step: call sph_enable_pass_timing(h, 1) and sph_step first");
+    CK(cudaEventSynchronize(h->ev.e[4]));
+    for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&h->pass_ms[k], h->ev.e[k], h->ev.e[k + 1]));
+    std::memcpy(ms4, h->pass_ms, sizeof h->pass_ms);
+    return SPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+// Shared device-side types and exact-arithmetic helpers for the SPH step kernels.
+//
+// Parity rule for this file: every floating-point operation that decides a neighbour or feeds a
+// reference-visible field is written with a round-to-nearest intrinsic (__fmul_rn, __fadd_rn,
+// __fdiv_rn, __fsqrt_rn, __dmul_rn, __dadd_rn). Those are never contracted into FMAs, so the
+// results match the reference's x86-64 (no-FMA) arithmetic operation for operation. The
+// library is additionally compiled with --fmad=false.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sphb {
+
+// ---- pos.w / vel.w bit lanes --------------------------------------------------------------
+// pos.w carries, as raw bits: [15:0] hash16 of the particle's start-of-step cell,
+// bit 16 "the 27 neighbour-cell hashes of this cell are not all distinct" (the reference then
+// visits some bucket more than once, src/sph.cpp:40-65), bit 17 "ghost" (slab halo copy).
+// vel.w carries the particle id as raw bits.
+constexpr uint32_t W_HASH_MASK = 0xFFFFu;
+constexpr uint32_t W_DUP = 1u << 16;
+constexpr uint32_t W_GHOST = 1u << 17;
+
+// Multipliers of getHash (reference src/neighborTable.cpp:8-10).
+constexpr uint32_t HASH_MX = 73856093u, HASH_MY = 19349663u, HASH_MZ = 83492791u;
+constexpr uint32_t REF_TABLE_SIZE = 262144u;  // src/neighborTable.h:9
+constexpr uint32_t REF_NO_PARTICLE = 0xFFFFFFFFu;
+
+// Dense cell grid of one step. Index = (ix * nz + iz) * ny + iy: y fastest, x slowest, so the
+// three y-neighbours of a cell are adjacent in the sorted particle array and an x-slab is one
+// contiguous range. Layers 0 and n-1 of every axis are empty padding; particles whose true cell
+// lies outside are clamped into layers 1 / n-2 (candidates become a superset, results do not
+// change because acceptance is by distance).
+struct GridDesc {
+    int ox, oy, oz;   // true cell coordinate of grid index 0 on each axis
+    int nx, ny, nz;   // cells per axis including padding
+    uint32_t ncells;  // nx * ny * nz
+    uint32_t sx, sz;  // index strides of x and z (sy == 1)
+    uint32_t pad_;
+};
+
+// Device-resident mutable counters shared by the kernels of a step.
+struct StepCounters {
+    int bbox[2][6];       // [parity][minx,miny,minz,maxx,maxy,maxz] of true cells
+    uint32_t ticket;      // tile ticket of the scan
+    uint32_t clamped;     // particles clamped into the grid this step
+    uint32_t aux[4];
+};
+
+// Settings + derived constants, passed to kernels by value.
+struct Params {
+    float h, h2, mass, mass_poly6, self_dens, gas_constant, rest_density;
+    float visc_mass;    // settings.viscosity * settings.mass  (src/sph.cpp:120, left-assoc)
+    float spiky_grad, spiky_lap, g;
+    float h_minus_box;  // settings.h - boxWidth               (src/sph.cpp:158,168)
+    float box_minus_h;  // -settings.h + boxWidth              (src/sph.cpp:163,173)
+    float two_h;        // 2 * settings.h                      (src/sph.cpp:154)
+    float two_hmb;      // 2 * (settings.h - boxWidth)         (src/sph.cpp:159,169)
+    float two_nhmb;     // 2 * -(settings.h - boxWidth)        (src/sph.cpp:164,174)
+    float wall_offset, elasticity, sphere_scale;
+};
+
+// ---- cell and hash (bit-exact targets) ----------------------------------------------------
+
+// getCell, src/neighborTable.cpp:14-17: IEEE fp32 divide, then truncation toward zero.
+__device__ __forceinline__ int cell_of(float x, float h) { return __float2int_rz(__fdiv_rn(x, h)); }
+
+// getHash narrowed to the uint16_t every consumer stores it in (src/neighborTable.cpp:5-12,
+// src/Particle.h:9): "% 262144" followed by the 16-bit store is "& 0xFFFF".
+__device__ __forceinline__ uint32_t hash16_of(int cx, int cy, int cz)
+{
+    return (((uint32_t)cx * HASH_MX) ^ ((uint32_t)cy * HASH_MY) ^ ((uint32_t)cz * HASH_MZ)) & W_HASH_MASK;
+}
+
+// True when two of the 27 offsets around (cx,cy,cz) share a hash16. hash(o) = a[ox]^b[oy]^c[oz]
+// with a,b,c the per-axis products, so two offsets collide iff the xor of one per-axis
+// difference from each axis is zero; per axis the differences are {0, a0^a1, a1^a2, a0^a2}.
+__device__ __forceinline__ bool nbhd_has_duplicate_hash(int cx, int cy, int cz)
+{
+    uint32_t a[3], b[3], c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a[k] = ((uint32_t)(cx + k - 1) * HASH_MX) & W_HASH_MASK;
+        b[k] = ((uint32_t)(cy + k - 1) * HASH_MY) & W_HASH_MASK;
+        c[k] = ((uint32_t)(cz + k - 1) * HASH_MZ) & W_HASH_MASK;
+    }
+    const uint32_t da[4] = {0u, a[0] ^ a[1], a[1] ^ a[2], a[0] ^ a[2]};
+    const uint32_t db[4] = {0u, b[0] ^ b[1], b[1] ^ b[2], b[0] ^ b[2]};
+    const uint32_t dc[4] = {0u, c[0] ^ c[1], c[1] ^ c[2], c[0] ^ c[2]};
+    bool dup = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i == 0 && j == 0) continue;  // same x and y offset: z offsets always differ in hash
+            const uint32_t t = da[i] ^ db[j];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dup |= (t == dc[k]);
+        }
+    return dup;
+}
+
+// How many of the 27 buckets the reference walks for a particle in cell (cx,cy,cz) are the
+// bucket `hj` — i.e. how many times a neighbour whose hash16 is hj gets accepted
+// (src/sph.cpp:40-65).
+__device__ __noinline__ uint32_t bucket_multiplicity(int cx, int cy, int cz, uint32_t hj)
+{
+    uint32_t m = 0;
+    for (int x = -1; x <= 1; ++x)
+        for (int y = -1; y <= 1; ++y)
+            for (int z = -1; z <= 1; ++z) m += (hash16_of(cx + x, cy + y, cz + z) == hj);
+    return m;
+}
+
+// Grid index of a true cell, clamped into the non-padding layers.
+__device__ __forceinline__ uint32_t grid_index(const GridDesc &g, int cx, int cy, int cz, bool &clamped)
+{
+    long long ix = (long long)cx - g.ox, iy = (long long)cy - g.oy, iz = (long long)cz - g.oz;
+    const long long jx = min(max(ix, 1LL), (long long)g.nx - 2);
+    const long long jy = min(max(iy, 1LL), (long long)g.ny - 2);
+    const long long jz = min(max(iz, 1LL), (long long)g.nz - 2);
+    clamped = (jx != ix) | (jy != iy) | (jz != iz);
+    return (uint32_t)((jx * g.nz + jz) * g.ny + jy);
+}
+
+// glm::length2(pj - pi): (dx*dx + dy*dy) + dz*dz, every operation rounded (src/sph.cpp:57,107).
+__device__ __forceinline__ float dist2_rn(float dx, float dy, float dz)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---- small warp helpers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+}  // namespace sphb

@@ -1,0 +1,278 @@
+// Neighbour-search build: cell bounding box -> dense grid plan -> per-cell histogram ->
+// exclusive scan (cell start offsets) -> placement -> stable order -> gather of the particle
+// arrays into cell-sorted SoA float4 rows.
+//
+// This replaces, in the reference: parallelCalculateHashes (src/sph.cpp:17-24), sortParticles
+// (src/sph.cpp:184-192) and createNeighborTable (src/neighborTable.cpp:19-37). The reference
+// sorts by the truncated 16-bit hash and walks whole hash buckets; here particles are counting-
+// sorted by their TRUE cell on a dense grid, so a particle's 27 neighbour cells are 9 contiguous
+// runs of the sorted array and bucket-mates from unrelated cells are never touched. The hash16
+// the reference would have stored is still computed bit-exactly and kept in pos.w, both as a
+// parity artefact and because it decides the reference's double-count rule (sph_device.cuh).
+#pragma once
+
+#include "sph_device.cuh"
+
+namespace sphb {
+
+constexpr int GRID_THREADS = 256;
+
+// ---- bounding box of true cells -----------------------------------------------------------
+
+__device__ __forceinline__ void bbox_accumulate(int *bb, int cx, int cy, int cz, bool valid)
+{
+    const int big = 0x7fffffff;
+    int mnx = valid ? cx : big, mny = valid ? cy : big, mnz = valid ? cz : big;
+    int mxx = valid ? cx : -big - 1, mxy = valid ? cy : -big - 1, mxz = valid ? cz : -big - 1;
+    mnx = __reduce_min_sync(0xffffffffu, mnx);
+    mny = __reduce_min_sync(0xffffffffu, mny);
+    mnz = __reduce_min_sync(0xffffffffu, mnz);
+    mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mxy = __reduce_max_sync(0xffffffffu, mxy);
+    mxz = __reduce_max_sync(0xffffffffu, mxz);
+    if ((threadIdx.x & 31) == 0) {
+        // Plain reads first: the box is monotone, so a stale value only costs a redundant atomic.
+        if (mnx < bb[0]) atomicMin(&bb[0], mnx);
+        if (mny < bb[1]) atomicMin(&bb[1], mny);
+        if (mnz < bb[2]) atomicMin(&bb[2], mnz);
+        if (mxx > bb[3]) atomicMax(&bb[3], mxx);
+        if (mxy > bb[4]) atomicMax(&bb[4], mxy);
+        if (mxz > bb[5]) atomicMax(&bb[5], mxz);
+    }
+}
+
+__global__ void __launch_bounds__(GRID_THREADS)
+k_bbox(const float4 *__restrict__ pos, uint32_t n, float h, StepCounters *ctr, int parity)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    int cx = 0, cy = 0, cz = 0;
+    if (valid) {
+        const float4 p = pos[i];
+        cx = cell_of(p.x, h); cy = cell_of(p.y, h); cz = cell_of(p.z, h);
+    }
+    bbox_accumulate(ctr->bbox[parity], cx, cy, cz, valid);
+}
+
+__global__ void k_reset_bbox(StepCounters *ctr, int parity)
+{
+    if (threadIdx.x < 3) ctr->bbox[parity][threadIdx.x] = 0x7fffffff;
+    else if (threadIdx.x < 6) ctr->bbox[parity][threadIdx.x] = -0x7fffffff - 1;
+}
+
+// ---- plan: bounding box -> GridDesc -------------------------------------------------------
+
+// One thread. Reads bbox[parity] (filled by the previous step's integration or by k_bbox after
+// an upload), writes the grid description of this step, re-arms bbox[parity^1] for the
+// integration kernel of this step and resets the per-step counters.
+__global__ void k_plan(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int *b = ctr->bbox[parity];
+    long long lo[3] = {b[0], b[1], b[2]};
+    long long dim[3];
+    for (int a = 0; a < 3; ++a) {
+        long long ext = (long long)b[3 + a] - lo[a] + 1;  // occupied cells on this axis
+        if (ext < 1) ext = 1;                              // empty box (n == 0)
+        dim[a] = ext + 2;                                  // one padding layer on both sides
+    }
+    // Keep the dense grid within its allocation: clip the high side of the longest axis until
+    // it fits. Clipped particles are clamped into the last interior layer by grid_index().
+    while (dim[0] * dim[1] * dim[2] > (long long)max_cells) {
+        int a = 1;  // prefer clipping y (the only unbounded axis: there is no ceiling)
+        if (dim[0] > dim[a]) a = 0;
+        if (dim[2] > dim[a]) a = 2;
+        dim[a] = max(3LL, (dim[a] + 1) / 2);
+        if (dim[0] == 3 && dim[1] == 3 && dim[2] == 3) break;
+    }
+    gd->ox = (int)max(lo[0] - 1, (long long)(-0x7fffffff - 1));
+    gd->oy = (int)max(lo[1] - 1, (long long)(-0x7fffffff - 1));
+    gd->oz = (int)max(lo[2] - 1, (long long)(-0x7fffffff - 1));
+    gd->nx = (int)dim[0]; gd->ny = (int)dim[1]; gd->nz = (int)dim[2];
+    gd->ncells = (uint32_t)(dim[0] * dim[1] * dim[2]);
+    gd->sz = (uint32_t)dim[1];
+    gd->sx = (uint32_t)(dim[1] * dim[2]);
+    ctr->ticket = 0;
+    ctr->clamped = 0;
+    int *nb = ctr->bbox[parity ^ 1];
+    nb[0] = nb[1] = nb[2] = 0x7fffffff;
+    nb[3] = nb[4] = nb[5] = -0x7fffffff - 1;
+}
+
+// ---- histogram ------------------------------------------------------------------------------
+
+// Zero counts[0 .. ncells] (the extra entry becomes the end sentinel after the scan).
+__global__ void __launch_bounds__(GRID_THREADS) k_zero_cells(uint32_t *__restrict__ counts, const GridDesc *__restrict__ gd)
+{
+    const uint32_t n = gd->ncells + 1;
+    const uint32_t n4 = n >> 2;
+    uint4 *c4 = reinterpret_cast<uint4 *>(counts);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+        c4[i] = make_uint4(0, 0, 0, 0);
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) counts[(n4 << 2) + threadIdx.x] = 0;
+}
+
+// One thread per particle (array is in last step's cell order, so neighbouring threads hit the
+// same or adjacent counters): cell -> grid index -> rank within the cell by atomicAdd.
+__global__ void __launch_bounds__(GRID_THREADS)
+k_cell_hist(const float4 *__restrict__ pos, uint32_t n, float h, const GridDesc *__restrict__ gd,
+            uint32_t *__restrict__ counts, uint2 *__restrict__ cell_rank, StepCounters *ctr)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const GridDesc g = *gd;
+    const float4 p = pos[i];
+    bool clamped;
+    const uint32_t c = grid_index(g, cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h), clamped);
+    const uint32_t r = atomicAdd(&counts[c], 1u);
+    cell_rank[i] = make_uint2(c, r);
+    if (clamped) atomicAdd(&ctr->clamped, 1u);
+}
+
+// ---- single-pass exclusive scan (decoupled look-back) ---------------------------------------
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr uint32_t SCAN_AGG = 1, SCAN_INCL = 2;
+
+__device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, uint32_t status, uint32_t v)
+{
+    return ((unsigned long long)(epoch & 0x3fffffffu) << 34) | ((unsigned long long)status << 32) | v;
+}
+
+// In-place exclusive scan of data[0 .. n) where n = *n_ptr + 1. Tiles are handed out by an atomic
+// ticket so a tile only ever waits on tiles that are already running; tile_state words carry an
+// epoch so they never need clearing between steps.
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_exclusive(uint32_t *__restrict__ data, const uint32_t *__restrict__ n_ptr,
+                 unsigned long long *tile_state, uint32_t *ticket, uint32_t epoch)
+{
+    __shared__ uint32_t s_tile, s_excl;
+    __shared__ uint32_t s_wsum[SCAN_THREADS / 32];
+    const uint32_t n = *n_ptr + 1;
+    const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) return;
+
+        const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        if (base + SCAN_ITEMS <= n) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(data + base);
+            const uint4 b = *reinterpret_cast<const uint4 *>(data + base + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < n) ? data[base + k] : 0u;
+        }
+        uint32_t tsum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) tsum += v[k];
+        const uint32_t inc = warp_incl_scan(tsum, lane);
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+
+        if (warp == 0) {
+            const uint32_t w = lane < SCAN_THREADS / 32 ? s_wsum[lane] : 0u;
+            const uint32_t winc = warp_incl_scan(w, lane);
+            const uint32_t total = __shfl_sync(0xffffffffu, winc, SCAN_THREADS / 32 - 1);
+            if (lane < SCAN_THREADS / 32) s_wsum[lane] = winc - w;
+            uint32_t excl = 0;
+            volatile unsigned long long *st = tile_state;
+            if (tile == 0) {
+                if (lane == 0) st[0] = scan_pack(epoch, SCAN_INCL, total);
+            } else {
+                if (lane == 0) st[tile] = scan_pack(epoch, SCAN_AGG, total);
+                int look = (int)tile - 1;
+                for (;;) {
+                    const int idx = look - lane;
+                    unsigned long long s = idx >= 0 ? st[idx] : scan_pack(epoch, SCAN_INCL, 0u);
+                    const uint32_t status = (uint32_t)(s >> 32) & 3u;
+                    const bool ready = ((uint32_t)(s >> 34) == (epoch & 0x3fffffffu)) && status != 0u;
+                    if (!__all_sync(0xffffffffu, ready)) continue;
+                    const uint32_t incl_mask = __ballot_sync(0xffffffffu, status == SCAN_INCL);
+                    const int first = incl_mask ? __ffs(incl_mask) - 1 : 32;
+                    uint32_t contrib = lane <= first ? (uint32_t)s : 0u;
+                    contrib = __reduce_add_sync(0xffffffffu, contrib);
+                    excl += contrib;
+                    if (incl_mask) break;
+                    look -= 32;
+                }
+                if (lane == 0) st[tile] = scan_pack(epoch, SCAN_INCL, excl + total);
+            }
+            if (lane == 0) s_excl = excl;
+        }
+        __syncthreads();
+
+        uint32_t run = s_excl + s_wsum[warp] + (inc - tsum);
+        uint32_t o[SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) { o[k] = run; run += v[k]; }
+        if (base + SCAN_ITEMS <= n) {
+            *reinterpret_cast<uint4 *>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4 *>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k)
+                if (base + k < n) data[base + k] = o[k];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- placement and stable order -------------------------------------------------------------
+
+// slot[start[cell] + rank] = source row. Within a cell the rank came from atomicAdd, so the
+// order inside a cell segment is arbitrary at this point.
+__global__ void __launch_bounds__(GRID_THREADS)
+k_place(const uint2 *__restrict__ cell_rank, uint32_t n, const uint32_t *__restrict__ starts,
+        uint32_t *__restrict__ slot_src)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 cr = cell_rank[i];
+    slot_src[starts[cr.x] + cr.y] = i;
+}
+
+// Make the order inside every cell segment ascending in source row (== a stable counting sort,
+// hence deterministic run to run): each slot counts the smaller entries of its own segment.
+__global__ void __launch_bounds__(GRID_THREADS)
+k_stable_order(const uint32_t *__restrict__ slot_src, const uint2 *__restrict__ cell_rank, uint32_t n,
+               const uint32_t *__restrict__ starts, uint32_t *__restrict__ order)
+{
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const uint32_t src = slot_src[d];
+    const uint32_t c = cell_rank[src].x;
+    const uint32_t s = starts[c], e = starts[c + 1];
+    uint32_t k = 0;
+    for (uint32_t t = s; t < e; ++t) k += (slot_src[t] < src);
+    order[s + k] = src;
+}
+
+// Gather rows into cell order; attach hash16 + duplicate flag to pos.w (vel.w keeps the id).
+__global__ void __launch_bounds__(GRID_THREADS)
+k_gather_sorted(const uint32_t *__restrict__ order, uint32_t n, float h,
+                const float4 *__restrict__ pos_in, const float4 *__restrict__ vel_in,
+                float4 *__restrict__ pos_out, float4 *__restrict__ vel_out)
+{
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const uint32_t src = order[d];
+    float4 p = pos_in[src];
+    const float4 v = vel_in[src];
+    const int cx = cell_of(p.x, h), cy = cell_of(p.y, h), cz = cell_of(p.z, h);
+    uint32_t w = hash16_of(cx, cy, cz) | (__float_as_uint(p.w) & W_GHOST);
+    if (nbhd_has_duplicate_hash(cx, cy, cz)) w |= W_DUP;
+    p.w = __uint_as_float(w);
+    pos_out[d] = p;
+    vel_out[d] = v;
+}
+
+}  // namespace sphb

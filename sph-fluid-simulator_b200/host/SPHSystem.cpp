@@ -1,0 +1,246 @@
+// Host-side mirror of the reference's SPHSystem class over the C-ABI. See SPHSystem.h.
+#include "SPHSystem.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+namespace sphb200 {
+
+namespace {
+void check(int rc, sph_handle *h, const char *what)
+{
+    if (rc != SPH_OK)
+        throw std::runtime_error(std::string(what) + ": " + sph_last_error(h));
+}
+}  // namespace
+
+SPHSettings::SPHSettings(float mass, float restDensity, float gasConst, float viscosity, float h,
+                         float g, float tension)
+    : gasConstant(gasConst), mass(mass), restDensity(restDensity), viscosity(viscosity), h(h), g(g),
+      tension(tension)
+{
+    sph_settings s = abi();
+    sph_derived d;
+    sph_settings_derive(&s, &d);
+    poly6 = d.poly6;
+    spikyGrad = d.spiky_grad;
+    spikyLap = d.spiky_lap;
+    h2 = d.h2;
+    selfDens = d.self_dens;
+    massPoly6Product = d.mass_poly6;
+    sphereScale = d.sphere_scale;
+}
+
+sph_settings SPHSettings::abi() const
+{
+    sph_settings s;
+    sph_settings_default(&s);  // dt, box, elasticity, wall offset: the reference's buried constants
+    s.mass = mass;
+    s.rest_density = restDensity;
+    s.gas_constant = gasConstant;
+    s.viscosity = viscosity;
+    s.h = h;
+    s.g = g;
+    s.tension = tension;
+    return s;
+}
+
+// ---- scenes -------------------------------------------------------------------------------------
+
+// Jitter of src/SPHSystem.cpp:83-91: (float(rand()) / float(RAND_MAX) * 0.5f - 1) * h / 10.
+static inline float jitter(float h)
+{
+    return (float(std::rand()) / float(RAND_MAX) * 0.5f - 1) * h / 10;
+}
+
+void sceneCube(size_t w, float h, float *pos, float *vel)
+{
+    std::srand(1024);
+    const float sep = h + 0.01f;
+    for (size_t i = 0; i < w; i++)
+        for (size_t j = 0; j < w; j++)
+            for (size_t k = 0; k < w; k++) {
+                const float rx = jitter(h), ry = jitter(h), rz = jitter(h);
+                const size_t idx = i + (j + w * k) * w;
+                pos[3 * idx + 0] = int(i) * sep + rx - 1.5f;
+                pos[3 * idx + 1] = int(j) * sep + ry + h + 0.1f;
+                pos[3 * idx + 2] = int(k) * sep + rz - 1.5f;
+                vel[3 * idx + 0] = vel[3 * idx + 1] = vel[3 * idx + 2] = 0.f;
+            }
+}
+
+void sceneBlock(size_t nx, size_t ny, size_t nz, float sep, float x0, float y0, float z0, float h,
+                unsigned seed, float *pos, float *vel)
+{
+    std::srand(seed);
+    for (size_t i = 0; i < nx; i++)
+        for (size_t j = 0; j < ny; j++)
+            for (size_t k = 0; k < nz; k++) {
+                const float rx = jitter(h), ry = jitter(h), rz = jitter(h);
+                const size_t idx = i + (j + ny * k) * nx;
+                pos[3 * idx + 0] = int(i) * sep + rx + x0;
+                pos[3 * idx + 1] = int(j) * sep + ry + y0;
+                pos[3 * idx + 2] = int(k) * sep + rz + z0;
+                vel[3 * idx + 0] = vel[3 * idx + 1] = vel[3 * idx + 2] = 0.f;
+            }
+}
+
+// ---- SPHSystem ----------------------------------------------------------------------------------
+
+SPHSystem::SPHSystem(size_t particleCubeWidth, const SPHSettings &settings, const bool &runOnGPU,
+                     int device)
+    : settings(settings), particleCubeWidth(particleCubeWidth), started_(false), handle_(nullptr)
+{
+    if (!runOnGPU)
+        throw std::runtime_error("sphb200::SPHSystem has no CPU step: construct with runOnGPU = true");
+    particleCount = particleCubeWidth * particleCubeWidth * particleCubeWidth;
+    sph_settings s = settings.abi();
+    const int rc = sph_create(&s, particleCount ? particleCount : 1, device, &handle_);
+    if (rc != SPH_OK) throw std::runtime_error(std::string("sph_create: ") + sph_last_error(nullptr));
+    initParticles();
+    started_ = false;
+}
+
+SPHSystem::~SPHSystem()
+{
+    if (handle_) sph_destroy(handle_);
+}
+
+void SPHSystem::initParticles()
+{
+    std::vector<float> pos(3 * particleCount), vel(3 * particleCount);
+    sceneCube(particleCubeWidth, settings.h, pos.data(), vel.data());
+    check(sph_upload(handle_, particleCount, pos.data(), vel.data(), nullptr), handle_, "sph_upload");
+}
+
+void SPHSystem::update(float deltaTime)
+{
+    if (!started_) return;
+    // To increase system stability, a fixed deltaTime is set (src/SPHSystem.cpp:112-113).
+    deltaTime = 0.003f;
+    check(sph_step(handle_, deltaTime, 1), handle_, "sph_step");
+}
+
+void SPHSystem::reset()
+{
+    initParticles();
+    started_ = false;
+}
+
+void SPHSystem::startSimulation() { started_ = true; }
+
+const std::vector<float> &SPHSystem::positions()
+{
+    positions_.resize(4 * particleCount);
+    check(sph_read_positions(handle_, positions_.data()), handle_, "sph_read_positions");
+    return positions_;
+}
+
+const std::vector<float> &SPHSystem::modelMatrices()
+{
+    matrices_.resize(16 * particleCount);
+    check(sph_write_transforms(handle_, matrices_.data()), handle_, "sph_write_transforms");
+    return matrices_;
+}
+
+void SPHSystem::download(std::vector<float> &pos, std::vector<float> &vel)
+{
+    pos.resize(3 * particleCount);
+    vel.resize(3 * particleCount);
+    check(sph_download(handle_, SPH_ORDER_ID, pos.data(), vel.data(), nullptr, nullptr, nullptr, nullptr, nullptr),
+          handle_, "sph_download");
+}
+
+}  // namespace sphb200
+
+// ---- the class surface through the C-ABI (for non-C++ hosts and the tests) -----------------------
+
+struct sph_system {
+    sphb200::SPHSystem *sys;
+    std::string err;
+};
+
+static thread_local std::string g_system_error;
+
+extern "C" {
+
+int sph_scene_cube(int width, float h, float *host_pos_xyz, float *host_vel_xyz)
+{
+    if (width < 0 || !host_pos_xyz || !host_vel_xyz) return SPH_ERR_INVALID;
+    sphb200::sceneCube((size_t)width, h, host_pos_xyz, host_vel_xyz);
+    return SPH_OK;
+}
+
+int sph_scene_block(int nx, int ny, int nz, float sep, float x0, float y0, float z0, float h, unsigned seed,
+                    float *host_pos_xyz, float *host_vel_xyz)
+{
+    if (nx < 0 || ny < 0 || nz < 0 || !host_pos_xyz || !host_vel_xyz) return SPH_ERR_INVALID;
+    sphb200::sceneBlock((size_t)nx, (size_t)ny, (size_t)nz, sep, x0, y0, z0, h, seed, host_pos_xyz, host_vel_xyz);
+    return SPH_OK;
+}
+
+int sph_system_create(int cube_width, const sph_settings *s, int run_on_gpu, int device, sph_system **out)
+{
+    if (!out || !s || cube_width < 0) return SPH_ERR_INVALID;
+    *out = nullptr;
+    try {
+        sphb200::SPHSettings st(s->mass, s->rest_density, s->gas_constant, s->viscosity, s->h, s->g, s->tension);
+        sphb200::SPHSystem *sys = new sphb200::SPHSystem((size_t)cube_width, st, run_on_gpu != 0, device);
+        *out = new sph_system{sys, {}};
+        return SPH_OK;
+    } catch (const std::exception &e) {
+        g_system_error = e.what();
+        return SPH_ERR_STATE;
+    }
+}
+
+const char *sph_system_last_error(const sph_system *w) { return w ? w->err.c_str() : g_system_error.c_str(); }
+
+int sph_system_destroy(sph_system *w)
+{
+    if (!w) return SPH_ERR_INVALID;
+    delete w->sys;
+    delete w;
+    return SPH_OK;
+}
+
+#define SYS_TRY(...)                                    \
+    if (!w) return SPH_ERR_INVALID;                     \
+    try { __VA_ARGS__; return SPH_OK; }                 \
+    catch (const std::exception &e) { w->err = e.what(); return SPH_ERR_CUDA; }
+
+int sph_system_start(sph_system *w) { SYS_TRY(w->sys->startSimulation()) }
+int sph_system_update(sph_system *w, float dt) { SYS_TRY(w->sys->update(dt)) }
+int sph_system_reset(sph_system *w) { SYS_TRY(w->sys->reset()) }
+uint64_t sph_system_count(const sph_system *w) { return w ? w->sys->particleCount : 0; }
+sph_handle *sph_system_handle(sph_system *w) { return w ? w->sys->handle() : nullptr; }
+
+int sph_system_positions(sph_system *w, float *host_xyzw)
+{
+    SYS_TRY({
+        const std::vector<float> &p = w->sys->positions();
+        std::copy(p.begin(), p.end(), host_xyzw);
+    })
+}
+
+int sph_system_model_matrices(sph_system *w, float *host_mat4)
+{
+    SYS_TRY({
+        const std::vector<float> &m = w->sys->modelMatrices();
+        std::copy(m.begin(), m.end(), host_mat4);
+    })
+}
+
+int sph_system_download(sph_system *w, float *host_pos_xyz, float *host_vel_xyz)
+{
+    SYS_TRY({
+        std::vector<float> p, v;
+        w->sys->download(p, v);
+        std::copy(p.begin(), p.end(), host_pos_xyz);
+        std::copy(v.begin(), v.end(), host_vel_xyz);
+    })
+}
+
+}  // extern "C"

@@ -1,0 +1,10 @@
+"""Import alias for the package directory `sph-fluid-simulator_b200/` (not a valid identifier)."""
+import importlib
+import os
+import sys
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+_pkg = importlib.import_module("sph-fluid-simulator_b200")
+sys.modules[__name__] = _pkg

@@ -1,0 +1,236 @@
+"""GPU parity: the CUDA path, called through the C-ABI, against the golden fixtures minted from the
+reference and against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star):
+  * cell hashes, the hash table and neighbour multisets: bit-exact;
+  * density / pressure rel 1e-5, force 1e-3 of max(|F_i|, median|F|), position 1e-5, velocity 1e-4
+    per step from identical state (the reference's own summation-order noise is 1e-7 .. 2e-5);
+  * free-running: <= 10 steps at the same tolerances scaled, long runs statistically.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal, assert_fields_close, by_id, load_golden
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_STATES = ["cube15_step0.npz", "cube15_step100.npz", "cube15_step300.npz", "cube20_step200.npz"]
+
+
+def settings_from(sph, s7, dt):
+    s = sph.default_settings()
+    s.mass, s.rest_density, s.gas_constant, s.viscosity, s.h, s.g, s.tension = [float(v) for v in s7]
+    s.dt = float(dt)
+    return s
+
+
+def neighbor_sets_gpu(sim):
+    ids, counts, offsets, lst = sim.neighbor_lists()
+    out = {}
+    for r in range(len(ids)):
+        out[int(ids[r])] = np.sort(lst[int(offsets[r]):int(offsets[r + 1])])
+    return out
+
+
+def neighbor_sets_oracle(oracle, os_, pos):
+    order, counts, cand, offsets, lst = oracle.neighbor_lists(os_, pos)
+    out = {}
+    for k in range(len(order)):
+        out[int(order[k])] = np.sort(order[lst[int(offsets[k]):int(offsets[k + 1])]])
+    return out, counts, cand
+
+
+@pytest.mark.parametrize("name", GOLDEN_STATES)
+def test_single_step_against_golden(sph, name):
+    g = load_golden(name)
+    s = settings_from(sph, g["settings"], g["dt"])
+    sim = sph.Sim(s, capacity=g["pos0"].shape[0])
+    sim.upload(g["pos0"], g["vel0"])
+    sim.step(1)
+    got = sim.download(sph.ORDER_ID)
+    want = by_id({k[:-1]: g[k] for k in ("pos1", "vel1", "force1", "density1", "pressure1", "hash1", "id1")})
+    # bit-exact: start-of-step hash16 of every particle, and the hash -> first index table
+    assert np.array_equal(got["hash"], want["hash"])
+    assert np.array_equal(sim.hash_table(), g["table1"])
+    assert_fields_close(got, want, name, gas_constant=s.gas_constant)
+    # the reference's order class: sorted by hash16 (any order inside a bucket)
+    h16 = sim.download(sph.ORDER_HASH16)
+    assert np.array_equal(h16["hash"], g["hash1"])
+    assert np.array_equal(np.sort(h16["id"]), np.arange(len(h16["id"])))
+    sim.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_STATES)
+def test_neighbor_multisets_bit_exact(sph, oracle, name):
+    g = load_golden(name)
+    s = settings_from(sph, g["settings"], g["dt"])
+    os_ = oracle.settings(tuple(float(v) for v in g["settings"]))
+    sim = sph.Sim(s, capacity=g["pos0"].shape[0])
+    sim.upload(g["pos0"], g["vel0"])
+    gpu = neighbor_sets_gpu(sim)
+    ora, counts, _ = neighbor_sets_oracle(oracle, os_, g["pos0"])
+    assert len(gpu) == len(ora)
+    repeats = 0
+    for i, want in ora.items():
+        got = gpu[i]
+        assert np.array_equal(got, want), f"particle {i}: {got} vs {want}"
+        repeats += len(np.unique(want)) != len(want)
+    if name == "cube20_step200.npz":
+        assert repeats > 0, "fixture was chosen to contain hash-collision double counts"
+    sim.close()
+
+
+def test_free_running_ten_steps(sph):
+    g = load_golden("cube20_step200.npz")
+    s = settings_from(sph, g["settings"], g["dt"])
+    sim = sph.Sim(s, capacity=g["pos0"].shape[0])
+    sim.upload(g["pos0"], g["vel0"])
+    sim.step(int(g["free_steps"]))
+    got = sim.download(sph.ORDER_ID, fields=("pos", "vel", "density"))
+    inv = np.argsort(g["idN"])
+    # App. B, 10 free steps: max |dx| 5.5e-7, rel d(rho) 2.6e-6 for the reference against itself
+    assert np.abs(got["pos"] - g["posN"][inv]).max() < 2e-5
+    assert (np.abs(got["density"] - g["densityN"][inv]) / g["densityN"][inv]).max() < 1e-4
+    sim.close()
+
+
+def test_step_locked_against_oracle_dense(sph, oracle):
+    """64 000-particle cube: warm up on the GPU to a dense state, then 5 step-locked comparisons."""
+    s = sph.default_settings()
+    os_ = oracle.settings()
+    pos, vel = sph.scene_cube(40, s.h)
+    sim = sph.Sim(s, capacity=pos.shape[0])
+    sim.upload(pos, vel)
+    sim.step(300)
+    st = sim.stats()
+    assert st.nan_count == 0 and st.mean_density > 10.5  # the reference reaches 11.31 at step 300
+    for k in range(5):
+        cur = sim.download(sph.ORDER_ID, fields=("pos", "vel"))
+        want = by_id(oracle.step(os_, s.dt, cur["pos"], cur["vel"]))
+        sim.upload(cur["pos"], cur["vel"])
+        sim.step(1)
+        got = sim.download(sph.ORDER_ID)
+        assert np.array_equal(got["hash"], want["hash"])
+        assert_fields_close(got, want, f"dense step {k}")
+    sim.close()
+
+
+def test_dam_break_block_scaled_settings(sph, oracle):
+    """h = 0.075 scaling of the defaults (1 M dam-break recipe) on a small block."""
+    h = 0.075
+    s = sph.scaled_settings(h)
+    os_ = oracle.settings(s.as_tuple7())
+    sep = h * 16.0 / 15.0
+    pos, vel = sph.scene_block(16, 24, 20, sep, ((h - 8.0) + sep, h * 5.0 / 3.0, -10 * sep), h, 1024)
+    sim = sph.Sim(s, capacity=pos.shape[0])
+    sim.upload(pos, vel)
+    sim.step(400)
+    cur = sim.download(sph.ORDER_ID, fields=("pos", "vel"))
+    assert np.isfinite(cur["pos"]).all()
+    want = by_id(oracle.step(os_, s.dt, cur["pos"], cur["vel"]))
+    sim.upload(cur["pos"], cur["vel"])
+    gpu_sets = neighbor_sets_gpu(sim)
+    ora_sets, counts, _ = neighbor_sets_oracle(oracle, os_, cur["pos"])
+    assert counts.mean() > 1.0, "state should be interacting"
+    for i, w in ora_sets.items():
+        assert np.array_equal(gpu_sets[i], w)
+    sim.upload(cur["pos"], cur["vel"])
+    sim.step(1)
+    got = sim.download(sph.ORDER_ID)
+    assert np.array_equal(got["hash"], want["hash"])
+    assert_fields_close(got, want, "dam-break block", gas_constant=s.gas_constant)
+    sim.close()
+
+
+def test_transforms_and_positions_readout(sph):
+    g = load_golden("cube15_step100.npz")
+    s = settings_from(sph, g["settings"], g["dt"])
+    sim = sph.Sim(s, capacity=g["pos0"].shape[0])
+    sim.upload(g["pos0"], g["vel0"])
+    sim.step(1)
+    dev = sim.download(sph.ORDER_DEVICE, fields=("pos", "id"))
+    xyz1 = sim.read_positions()
+    assert_bit_equal(xyz1[:, :3], dev["pos"], "read_positions")
+    assert (xyz1[:, 3] == 1.0).all()
+    mats = sim.write_transforms()
+    inv = np.argsort(g["id1"])
+    want = g["transforms1"][inv][dev["id"]]
+    # scale part is exact; translation follows the position tolerance
+    assert np.array_equal(mats[:, [0, 5, 10, 15]], want[:, [0, 5, 10, 15]])
+    assert np.abs(mats - want).max() <= 1e-5
+    assert_bit_equal(mats[:, 12:15], dev["pos"], "translation column")
+    sim.close()
+
+
+def test_aos_drop_in_call(sph):
+    """sph_update_particles_aos == updateParticlesGPU's data contract (60-byte Particle rows)."""
+    g = load_golden("cube20_step200.npz")
+    s = settings_from(sph, g["settings"], g["dt"])
+    n = g["pos0"].shape[0]
+    rows = np.zeros((n, 15), np.uint32)
+    rows[:, 0:3] = g["pos0"].view(np.uint32)
+    rows[:, 3:6] = g["vel0"].view(np.uint32)
+    rows[:, 6] = np.arange(n, dtype=np.uint32)  # ids in the dead acceleration field, like the oracle harness
+    rows[:, 7] = 0xDEADBEEF
+    sim = sph.Sim(s, capacity=n)
+    mats = sim.update_particles_aos(rows, dt=float(g["dt"]))
+    # comes back sorted by start-of-step hash16 with the dead field carried through
+    assert np.array_equal(rows[:, 14], g["hash1"].astype(np.uint32))
+    assert (rows[:, 7] == 0xDEADBEEF).all()
+    got = dict(id=rows[:, 6].copy(), pos=rows[:, 0:3].copy().view(np.float32), vel=rows[:, 3:6].copy().view(np.float32),
+               force=rows[:, 9:12].copy().view(np.float32), density=rows[:, 12].copy().view(np.float32),
+               pressure=rows[:, 13].copy().view(np.float32))
+    assert_bit_equal(mats[:, 12:15], got["pos"], "transform rows follow particle rows")
+    want = by_id({k[:-1]: g[k] for k in ("pos1", "vel1", "force1", "density1", "pressure1", "id1")})
+    assert_fields_close(by_id(got), want, "aos", gas_constant=s.gas_constant)
+    sim.close()
+
+
+def test_sphsystem_class_surface(sph):
+    g = load_golden("class_surface.npz")
+    init = load_golden("init_cube_w15.npz")
+    sys_ = sph.System(15)
+    assert sys_.particleCount == 3375
+    for _ in range(5):
+        sys_.update(0.016)  # not started: no-op (src/SPHSystem.cpp:111)
+    pos, vel = sys_.download()
+    assert_bit_equal(pos, g["pos_not_started"], "update before startSimulation")
+    assert_bit_equal(pos, init["pos"], "initParticles")
+    sys_.startSimulation()
+    for _ in range(20):
+        sys_.update(0.5)  # caller's dt is ignored, 0.003 is used (src/SPHSystem.cpp:113)
+    pos, vel = sys_.download()
+    assert np.abs(pos - g["pos_after20"]).max() <= 1e-5
+    assert np.abs(vel - g["vel_after20"]).max() <= 1e-4
+    assert sys_.positions().shape == (3375, 4) and sys_.model_matrices().shape == (3375, 16)
+    sys_.reset()
+    pos, vel = sys_.download()
+    assert_bit_equal(pos, g["pos_after_reset"], "reset")
+    sys_.update(0.016)  # reset stops the simulation (src/SPHSystem.cpp:138)
+    assert_bit_equal(sys_.download()[0], g["pos_after_reset"], "update after reset")
+    sys_.close()
+    with pytest.raises(sph.SphError):
+        sph.System(15, run_on_gpu=False)
+
+
+def test_long_run_statistics(sph, oracle):
+    """Chaotic beyond ~50 steps: compare statistics only (App. B: mean density within 2 %, KE 1 %)."""
+    s = sph.default_settings()
+    os_ = oracle.settings()
+    pos, vel = sph.scene_cube(24, s.h)
+    n = pos.shape[0]
+    sim = sph.Sim(s, capacity=n)
+    sim.upload(pos, vel)
+    sim.step(250)
+    got = sim.download(sph.ORDER_ID, fields=("vel", "density"))
+    st = sim.stats()
+    p, v = pos, vel
+    for _ in range(250):
+        o = oracle.step(os_, s.dt, p, v)
+        p, v = o["pos"], o["vel"]
+    ke_o = 0.5 * s.mass * float((o["vel"].astype(np.float64) ** 2).sum())
+    assert st.nan_count == 0
+    assert abs(st.mean_density - o["density"].mean()) / o["density"].mean() < 0.02
+    assert abs(st.kinetic_energy - ke_o) / ke_o < 0.01
+    assert abs(float(got["density"].mean()) - st.mean_density) < 1e-3
+    sim.close()

@@ -1,0 +1,5 @@
+set -x
+nvidia-smi -L
+cd $GRAFT_REPO_ROOT
+make -s -C oracle oracle
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -40
