@@ -172,11 +172,21 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
 
 int sph_get_stats(sph_handle *h, sph_stats *out);
 
-/* Per-pass device times in milliseconds for the most recent sph_step call's LAST step, measured
- * with CUDA events when enabled (replaces the Timer blocks of src/sph.cpp:235,249,262).
- * Order: grid build (hash+sort+ranges), density, forces, integrate. */
+/* Per-pass device times (replaces the Timer blocks of src/sph.cpp:235,249,262). While enabled,
+ * every step records CUDA events between its passes; sph_pass_times synchronises, returns the
+ * MEAN milliseconds per step over the steps recorded since the last call (or since enabling) in
+ * the order: grid build (hash + sort + cell ranges), density, forces, integrate — and how many
+ * steps that was — then starts a new window. At most 16384 steps are kept per window. */
 int sph_enable_pass_timing(sph_handle *h, int enable);
-int sph_pass_times(sph_handle *h, float *ms4);
+int sph_pass_times(sph_handle *h, float *ms4, uint64_t *steps_out);
+
+/* Kernels launched so far by sph_step / sph_update_particles_aos on this handle. */
+uint64_t sph_launch_count(const sph_handle *h);
+
+/* Device self-test: the force pass divides with a reciprocal shared between numerators of equal
+ * denominator (csrc/sph_physics.cuh, Recip); this checks it bit-for-bit against IEEE division on
+ * n pseudo-random pairs and returns the number of mismatches (expected 0). */
+int sph_selftest_division(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out);
 
 /* Raw CUDA stream of the handle (cudaStream_t as void*), so a caller can order its own work or
  * record events on it. */

@@ -93,7 +93,9 @@ def load_library() -> C.CDLL:
         "sph_neighbor_lists": ([hp, u32p, u64p, u32p, C.c_uint64, u32p], C.c_int),
         "sph_get_stats": ([hp, C.POINTER(Stats)], C.c_int),
         "sph_enable_pass_timing": ([hp, C.c_int], C.c_int),
-        "sph_pass_times": ([hp, fp], C.c_int),
+        "sph_pass_times": ([hp, fp, u64p], C.c_int),
+        "sph_launch_count": ([hp], C.c_uint64),
+        "sph_selftest_division": ([hp, C.c_uint64, C.c_uint64, u64p], C.c_int),
         "sph_stream": ([hp], C.c_void_p),
         "sph_scene_cube": ([C.c_int, C.c_float, fp, fp], C.c_int),
         "sph_scene_block": ([C.c_int] * 3 + [C.c_float] * 5 + [C.c_uint, fp, fp], C.c_int),
@@ -294,9 +296,22 @@ class Sim:
         self._ck(self.lib.sph_enable_pass_timing(self._h, int(on)))
 
     def pass_times(self):
+        """Mean ms per step of each pass over the window since the last call, and the window size."""
         out = np.empty(4, np.float32)
-        self._ck(self.lib.sph_pass_times(self._h, _ptr(out, C.c_float)))
-        return dict(zip(("grid", "density", "forces", "integrate"), out.tolist()))
+        nsteps = C.c_uint64(0)
+        self._ck(self.lib.sph_pass_times(self._h, _ptr(out, C.c_float), C.byref(nsteps)))
+        d = dict(zip(("grid", "density", "forces", "integrate"), out.tolist()))
+        d["steps"] = int(nsteps.value)
+        return d
+
+    def selftest_division(self, n=1 << 22, seed=1) -> int:
+        bad = C.c_uint64(0)
+        self._ck(self.lib.sph_selftest_division(self._h, n, seed, C.byref(bad)))
+        return int(bad.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.sph_launch_count(self._h))
 
 
 class System:

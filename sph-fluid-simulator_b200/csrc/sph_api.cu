@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "sph_device.cuh"
 #include "sph_grid.cuh"
@@ -44,6 +45,7 @@ struct sph_handle {
     int cur = 0;
     float4 *force = nullptr;
     float *rho = nullptr;
+    uint32_t *nlist = nullptr, *ncount = nullptr;  // neighbour lists written by the density pass
     uint2 *cell_rank = nullptr;
     uint32_t *slot_src = nullptr, *order = nullptr, *map = nullptr;
     uint32_t *cells = nullptr;
@@ -62,10 +64,13 @@ struct sph_handle {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
 
+    // Per-pass CUDA-event timing (the Timer blocks of src/sph.cpp:235,249,262): one event set per
+    // timed step, drawn from a pool that grows on demand and is read back in sph_pass_times.
     bool timing = false;
-    PassEvents ev;
-    float pass_ms[4] = {0, 0, 0, 0};
-    bool pass_valid = false;
+    std::vector<PassEvents> ev_pool;
+    size_t ev_used = 0;
+    static constexpr size_t kMaxTimedSteps = 16384;
+    uint64_t launches = 0;  // kernels launched by sph_step / sph_update_particles_aos so far
 
     char err[512] = "";
 };
@@ -203,25 +208,38 @@ int build_grid(sph_handle *h)
     return SPH_OK;
 }
 
-int step_once(sph_handle *h, float dt, bool timed)
+int step_once(sph_handle *h, float dt)
 {
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
-    if (timed) CK(cudaEventRecord(h->ev.e[0], s));
+    bool timed = h->timing && h->ev_used < sph_handle::kMaxTimedSteps;
+    cudaEvent_t *ev = nullptr;
+    if (timed) {
+        if (h->ev_used == h->ev_pool.size()) {
+            PassEvents pe;
+            for (auto &e : pe.e) CK(cudaEventCreate(&e));
+            h->ev_pool.push_back(pe);
+        }
+        ev = h->ev_pool[h->ev_used++].e;
+    }
+    if (timed) CK(cudaEventRecord(ev[0], s));
     int rc = build_grid(h);
     if (rc) return rc;
-    if (timed) CK(cudaEventRecord(h->ev.e[1], s));
-    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->rho);
+    if (timed) CK(cudaEventRecord(ev[1], s));
+    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->rho,
+                                                                 h->nlist, h->ncount, (uint32_t)h->cap);
     CK_LAUNCH();
-    if (timed) CK(cudaEventRecord(h->ev.e[2], s));
+    if (timed) CK(cudaEventRecord(ev[2], s));
     k_forces<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->rho, n, h->gd,
-                                                                h->cells, h->P, h->force);
+                                                                h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap,
+                                                                h->force);
     CK_LAUNCH();
-    if (timed) CK(cudaEventRecord(h->ev.e[3], s));
+    if (timed) CK(cudaEventRecord(ev[3], s));
     k_integrate<<<blocks_for(n, 256), 256, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho, n, h->P, dt,
                                                   h->ctr, h->parity ^ 1);
     CK_LAUNCH();
-    if (timed) CK(cudaEventRecord(h->ev.e[4], s));
+    if (timed) CK(cudaEventRecord(ev[4], s));
+    h->launches += 10;  // plan, zero, hist, scan, place, stable order, gather, density, forces, integrate
     h->parity ^= 1;
     ++h->steps;
     h->have_step = true;
@@ -261,7 +279,6 @@ int after_upload(sph_handle *h, uint64_t n)
     h->steps = 0;
     h->have_state = true;
     h->have_step = false;
-    h->pass_valid = false;
     return compute_bbox(h);
 }
 
@@ -359,6 +376,8 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     }
     CKC(cudaMalloc(&nh->force, sizeof(float4) * cap));
     CKC(cudaMalloc(&nh->rho, sizeof(float) * cap));
+    CKC(cudaMalloc(&nh->nlist, sizeof(uint32_t) * cap * NLIST_ROWS));
+    CKC(cudaMalloc(&nh->ncount, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->cell_rank, sizeof(uint2) * cap));
     CKC(cudaMalloc(&nh->slot_src, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->order, sizeof(uint32_t) * cap));
@@ -376,7 +395,6 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaMalloc(&nh->stats_acc, sizeof(StatsAccum)));
     const uint32_t c65536 = 65536u;
     CKC(cudaMemcpyAsync(nh->const_65536, &c65536, sizeof c65536, cudaMemcpyHostToDevice, nh->stream));
-    for (auto &e : nh->ev.e) CKC(cudaEventCreate(&e));
     CKC(cudaStreamSynchronize(nh->stream));
 #undef CKC
     *out = nh;
@@ -389,11 +407,12 @@ int sph_destroy(sph_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int b = 0; b < 2; ++b) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); }
-    cudaFree(h->force); cudaFree(h->rho); cudaFree(h->cell_rank); cudaFree(h->slot_src);
+    cudaFree(h->force); cudaFree(h->rho); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot_src);
     cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
     cudaFree(h->stats_acc); cudaFree(h->scratch);
-    for (auto &e : h->ev.e) if (e) cudaEventDestroy(e);
+    for (auto &pe : h->ev_pool)
+        for (auto &e : pe.e) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SPH_OK;
@@ -587,10 +606,8 @@ int sph_step(sph_handle *h, float dt, int nsteps)
     if (!(dt > 0.f)) dt = h->settings.dt;  // SPHSystem::update's fixed step (src/SPHSystem.cpp:113)
     if (h->n == 0) return SPH_OK;
     for (int k = 0; k < nsteps; ++k) {
-        const bool timed = h->timing && k == nsteps - 1;
-        rc = step_once(h, dt, timed);
+        rc = step_once(h, dt);
         if (rc) return rc;
-        if (timed) h->pass_valid = true;
     }
     return SPH_OK;
 }
@@ -624,7 +641,7 @@ int sph_update_particles_aos(sph_handle *h, void *host_particles, float *host_ma
     CK_LAUNCH();
     rc = after_upload(h, n);
     if (rc) return rc;
-    rc = step_once(h, dt, false);
+    rc = step_once(h, dt);
     if (rc) return rc;
     rc = build_hash16_order(h, true);
     if (rc) return rc;
@@ -676,9 +693,14 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
     h->have_step = false;
     rc = build_grid(h);
     if (rc) return rc;
+    // The density pass writes the lists the force pass consumes; report exactly those.
+    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)n, h->gd, h->cells, h->P,
+                                                                         h->rho, h->nlist, h->ncount, (uint32_t)h->cap);
+    CK_LAUNCH();
     uint32_t *dcounts = h->slot_src;  // free after build_grid
     k_neighbor_lists<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)n,
-                                                                                h->gd, h->cells, h->P, dcounts, nullptr, nullptr);
+                                                                                h->gd, h->cells, h->P, h->nlist, h->ncount,
+                                                                                (uint32_t)h->cap, dcounts, nullptr, nullptr);
     CK_LAUNCH();
     CK(cudaMemcpyAsync(host_counts, dcounts, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
     if (host_ids_out) {
@@ -708,7 +730,8 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
     uint32_t *dlist = (uint32_t *)((char *)h->scratch + bo);
     CK(cudaMemcpyAsync(doff, host_offsets, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, h->stream));
     k_neighbor_lists<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)n,
-                                                                                h->gd, h->cells, h->P, dcounts, doff, dlist);
+                                                                                h->gd, h->cells, h->P, h->nlist, h->ncount,
+                                                                                (uint32_t)h->cap, dcounts, doff, dlist);
     CK_LAUNCH();
     CK(cudaMemcpyAsync(host_list, dlist, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -753,19 +776,61 @@ int sph_enable_pass_timing(sph_handle *h, int enable)
 {
     if (!h) return SPH_ERR_INVALID;
     h->timing = enable != 0;
-    h->pass_valid = false;
+    h->ev_used = 0;
     return SPH_OK;
 }
 
-int sph_pass_times(sph_handle *h, float *ms4)
+int sph_pass_times(sph_handle *h, float *ms4, uint64_t *steps_out)
 {
     int rc = enter(h);
     if (rc) return rc;
     if (!ms4) return fail(h, SPH_ERR_INVALID, "destination is NULL");
-    if (!h->pass_valid) return fail(h, SPH_ERR_STATE, "no timed step: call sph_enable_pass_timing(h, 1) and sph_step first");
-    CK(cudaEventSynchronize(h->ev.e[4]));
-    for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&h->pass_ms[k], h->ev.e[k], h->ev.e[k + 1]));
-    std::memcpy(ms4, h->pass_ms, sizeof h->pass_ms);
+    if (h->ev_used == 0)
+        return fail(h, SPH_ERR_STATE, "no timed step: call sph_enable_pass_timing(h, 1) and sph_step first");
+    CK(cudaStreamSynchronize(h->stream));
+    double acc[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i < h->ev_used; ++i)
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, h->ev_pool[i].e[k], h->ev_pool[i].e[k + 1]));
+            acc[k] += ms;
+        }
+    for (int k = 0; k < 4; ++k) ms4[k] = (float)(acc[k] / (double)h->ev_used);
+    if (steps_out) *steps_out = h->ev_used;
+    h->ev_used = 0;
+    return SPH_OK;
+}
+
+uint64_t sph_launch_count(const sph_handle *h) { return h ? h->launches : 0; }
+
+int sph_selftest_division(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!mismatches_out || n == 0 || n > (1ull << 28)) return fail(h, SPH_ERR_INVALID, "bad arguments");
+    // Log-uniform magnitudes over the ranges the force pass sees (and well beyond), both signs.
+    std::vector<float> a(n), d(n);
+    uint64_t x = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto next = [&]() { x = x * 6364136223846793005ull + 1442695040888963407ull; return (double)(x >> 11) / 9007199254740992.0; };
+    for (uint64_t i = 0; i < n; ++i) {
+        const double ea = -20.0 + 40.0 * next(), ed = -12.0 + 24.0 * next();
+        a[i] = (float)((next() < 0.5 ? -1.0 : 1.0) * std::pow(10.0, ea));
+        d[i] = (float)((next() < 0.5 ? -1.0 : 1.0) * std::pow(10.0, ed));
+    }
+    const size_t bytes = align_up(sizeof(float) * n, 256);
+    rc = ensure_scratch(h, 2 * bytes + 256);
+    if (rc) return rc;
+    float *da = (float *)h->scratch, *dd = (float *)((char *)h->scratch + bytes);
+    uint32_t *dout = (uint32_t *)((char *)h->scratch + 2 * bytes);
+    CK(cudaMemcpyAsync(da, a.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dd, d.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(dout, 0, sizeof(uint32_t), h->stream));
+    k_selftest_div<<<blocks_for(n, 256), 256, 0, h->stream>>>(da, dd, (uint32_t)n, dout);
+    CK_LAUNCH();
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, dout, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *mismatches_out = bad;
     return SPH_OK;
 }
 

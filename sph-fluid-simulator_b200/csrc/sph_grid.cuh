@@ -41,6 +41,40 @@ __device__ __forceinline__ void bbox_accumulate(int *bb, int cx, int cy, int cz,
     }
 }
 
+// Block-level variant for kernels that already run one thread per particle: warp reductions,
+// then one set of (at most six) atomics per block. The box is read with ld.cg so a stale L1 line
+// cannot make every block issue redundant atomics.
+__device__ __forceinline__ void bbox_accumulate_block(int *bb, int cx, int cy, int cz, bool valid)
+{
+    __shared__ int s_box[6][32];
+    const int big = 0x7fffffff;
+    int v[6] = {valid ? cx : big, valid ? cy : big, valid ? cz : big,
+                valid ? cx : -big - 1, valid ? cy : -big - 1, valid ? cz : -big - 1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = __reduce_min_sync(0xffffffffu, v[k]);
+#pragma unroll
+    for (int k = 3; k < 6; ++k) v[k] = __reduce_max_sync(0xffffffffu, v[k]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s_box[k][warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = lane < nwarps ? s_box[k][lane] : (k < 3 ? big : -big - 1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = __reduce_min_sync(0xffffffffu, v[k]);
+#pragma unroll
+        for (int k = 3; k < 6; ++k) v[k] = __reduce_max_sync(0xffffffffu, v[k]);
+        if (lane < 3) {
+            if (v[lane] < __ldcg(&bb[lane])) atomicMin(&bb[lane], v[lane]);
+        } else if (lane < 6) {
+            if (v[lane] > __ldcg(&bb[lane])) atomicMax(&bb[lane], v[lane]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(GRID_THREADS)
 k_bbox(const float4 *__restrict__ pos, uint32_t n, float h, StepCounters *ctr, int parity)
 {
@@ -51,7 +85,7 @@ k_bbox(const float4 *__restrict__ pos, uint32_t n, float h, StepCounters *ctr, i
         const float4 p = pos[i];
         cx = cell_of(p.x, h); cy = cell_of(p.y, h); cz = cell_of(p.z, h);
     }
-    bbox_accumulate(ctr->bbox[parity], cx, cy, cz, valid);
+    bbox_accumulate_block(ctr->bbox[parity], cx, cy, cz, valid);
 }
 
 __global__ void k_reset_bbox(StepCounters *ctr, int parity)

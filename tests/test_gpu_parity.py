@@ -213,6 +213,12 @@ def test_sphsystem_class_surface(sph):
         sph.System(15, run_on_gpu=False)
 
 
+def test_shared_reciprocal_division_is_ieee(sph):
+    sim = sph.Sim(sph.default_settings(), capacity=1024)
+    assert sim.selftest_division(1 << 23, seed=7) == 0
+    sim.close()
+
+
 def test_long_run_statistics(sph, oracle):
     """Chaotic beyond ~50 steps: compare statistics only (App. B: mean density within 2 %, KE 1 %)."""
     s = sph.default_settings()
