@@ -203,6 +203,10 @@ int sph_scene_cube(int width, float h, float *host_pos_xyz, float *host_vel_xyz)
 int sph_scene_block(int nx, int ny, int nz, float sep, float x0, float y0, float z0, float h, unsigned seed,
                     float *host_pos_xyz, float *host_vel_xyz);
 
+/* Rows i in [i0, i1) of that block and their global ids (one lattice x-range per rank). */
+int sph_scene_block_slice(int nx, int ny, int nz, float sep, float x0, float y0, float z0, float h, unsigned seed,
+                          int i0, int i1, float *host_pos_xyz, float *host_vel_xyz, uint32_t *host_ids);
+
 /* class SPHSystem (src/SPHSystem.h:24-57) for hosts that cannot include the C++ header
  * (sph-fluid-simulator_b200/host/SPHSystem.h): constructor, update, reset, startSimulation,
  * particleCount, and the renderer read-out that replaces `particles` / `sphereModelMtxs`.
@@ -219,6 +223,40 @@ sph_handle *sph_system_handle(sph_system *sys);
 int sph_system_positions(sph_system *sys, float *host_xyzw);        /* count rows of (x,y,z,1) */
 int sph_system_model_matrices(sph_system *sys, float *host_mat4);   /* count column-major mat4 */
 int sph_system_download(sph_system *sys, float *host_pos_xyz, float *host_vel_xyz); /* by particle id */
+
+
+/* ---- slab decomposition (one process per GPU; DESIGN.md "Multi-GPU") -------------------- */
+/*
+ * The reference has no multi-GPU path; this is new work. The domain is cut along
+ * x at cell boundaries: rank r owns the particles whose cell.x (reference getCell) lies in
+ * [cuts[r], cuts[r+1]); cuts has world+1 entries, cuts[0] / cuts[world] are treated as -inf / +inf.
+ * The library provides the device-side primitives; the exchange itself is the caller's (NCCL
+ * through torch.distributed in sph-fluid-simulator_b200/slab.py). Buffers are DEVICE memory.
+ * A particle row on the wire is two float4: (x, y, z, id bits) and (vx, vy, vz, 0) = 32 bytes.
+ * Per step: count + pack (migrants leave, last step's ghosts are dropped) -> append arrivals ->
+ * pack_halo both sides -> append ghosts -> step_density -> pack_halo_density -> exchange ->
+ * set_ghost_density -> step_forces.
+ */
+int sph_slab_enable(sph_handle *h, int enable);
+uint64_t sph_slab_owned(const sph_handle *h); /* rows that are not ghosts */
+/* counts[r] = live owned rows whose owner under `cuts` is rank r (host arrays). */
+int sph_slab_count(sph_handle *h, const int32_t *cuts, int world, uint64_t *host_counts);
+/* Copy the rows owned by rank r != self to dev_buf at row row_offsets[r] + k and drop them here. */
+int sph_slab_pack(sph_handle *h, const int32_t *cuts, int world, int self, void *dev_buf, const uint64_t *row_offsets);
+/* Append rows: kind 0 = owned arrivals, 1 / 2 = ghost batch of side 0 / 1 (one batch per side). */
+int sph_slab_append(sph_handle *h, const void *dev_rows, uint64_t nrows, int kind);
+/* Halo message of the owned rows in x-cell cell_x; remembers the rows for pack_halo_density. */
+int sph_slab_pack_halo(sph_handle *h, int32_t cell_x, int side, void *dev_buf, uint64_t capacity_rows, uint64_t *nrows_out);
+/* Grid build over owned + ghost rows, then density (and neighbour lists) of the owned rows. */
+int sph_slab_step_density(sph_handle *h);
+/* Densities (float) of the rows of halo message `side`, same order; nrows = that message's. */
+int sph_slab_pack_halo_density(sph_handle *h, int side, void *dev_buf);
+/* Densities for ghost batch `side`, in the order its rows were appended. */
+int sph_slab_set_ghost_density(sph_handle *h, int side, const void *dev_buf, uint64_t nrows);
+/* Forces + integration of the owned rows. */
+int sph_slab_step_forces(sph_handle *h, float dt);
+/* Histogram of cell.x over owned rows, bins [x_cell_lo, x_cell_lo + nbins), ends clamped. */
+int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, uint64_t *host_hist);
 
 #ifdef __cplusplus
 }

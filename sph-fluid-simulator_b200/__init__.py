@@ -12,5 +12,5 @@ or through the `sph_b200` alias module at the repository root.
 """
 from .binding import (  # noqa: F401
     ORDER_DEVICE, ORDER_HASH16, ORDER_ID, NO_PARTICLE, TABLE_SIZE, Derived, Settings, Sim, SphError, Stats,
-    System, build_library, default_settings, derive, load_library, scaled_settings, scene_block, scene_cube,
+    System, build_library, default_settings, derive, load_library, scaled_settings, scene_block, scene_block_slice, scene_cube,
 )

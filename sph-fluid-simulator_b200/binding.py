@@ -99,6 +99,18 @@ def load_library() -> C.CDLL:
         "sph_stream": ([hp], C.c_void_p),
         "sph_scene_cube": ([C.c_int, C.c_float, fp, fp], C.c_int),
         "sph_scene_block": ([C.c_int] * 3 + [C.c_float] * 5 + [C.c_uint, fp, fp], C.c_int),
+        "sph_slab_enable": ([hp, C.c_int], C.c_int),
+        "sph_slab_owned": ([hp], C.c_uint64),
+        "sph_slab_count": ([hp, C.POINTER(C.c_int32), C.c_int, u64p], C.c_int),
+        "sph_slab_pack": ([hp, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_void_p, u64p], C.c_int),
+        "sph_slab_append": ([hp, C.c_void_p, C.c_uint64, C.c_int], C.c_int),
+        "sph_slab_pack_halo": ([hp, C.c_int32, C.c_int, C.c_void_p, C.c_uint64, u64p], C.c_int),
+        "sph_slab_step_density": ([hp], C.c_int),
+        "sph_slab_pack_halo_density": ([hp, C.c_int, C.c_void_p], C.c_int),
+        "sph_slab_set_ghost_density": ([hp, C.c_int, C.c_void_p, C.c_uint64], C.c_int),
+        "sph_slab_step_forces": ([hp, C.c_float], C.c_int),
+        "sph_slab_xcell_histogram": ([hp, C.c_int32, C.c_uint32, u64p], C.c_int),
+        "sph_scene_block_slice": ([C.c_int] * 3 + [C.c_float] * 5 + [C.c_uint, C.c_int, C.c_int, fp, fp, u32p], C.c_int),
         "sph_system_create": ([C.c_int, sp, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
         "sph_system_destroy": ([hp], C.c_int),
         "sph_system_last_error": ([hp], C.c_char_p),
@@ -168,6 +180,19 @@ def scene_block(nx, ny, nz, sep, origin, h, seed=1024):
     if rc:
         raise SphError(rc, "sph_scene_block")
     return pos, vel
+
+
+def scene_block_slice(nx, ny, nz, sep, origin, h, seed, i0, i1):
+    n = (i1 - i0) * ny * nz
+    pos = np.empty((n, 3), np.float32)
+    vel = np.empty((n, 3), np.float32)
+    ids = np.empty(n, np.uint32)
+    rc = load_library().sph_scene_block_slice(nx, ny, nz, C.c_float(sep), C.c_float(origin[0]), C.c_float(origin[1]),
+                                              C.c_float(origin[2]), C.c_float(h), seed, i0, i1, _ptr(pos, C.c_float),
+                                              _ptr(vel, C.c_float), _ptr(ids, C.c_uint32))
+    if rc:
+        raise SphError(rc, "sph_scene_block_slice")
+    return pos, vel, ids
 
 
 class Sim:

@@ -17,6 +17,7 @@
 #include "sph_grid.cuh"
 #include "sph_physics.cuh"
 #include "sph_io.cuh"
+#include "sph_slab.cuh"
 
 using namespace sphb;
 
@@ -46,8 +47,15 @@ struct sph_handle {
     float4 *force = nullptr;
     float *rho = nullptr;
     uint32_t *nlist = nullptr, *ncount = nullptr;  // neighbour lists written by the density pass
-    uint2 *cell_rank = nullptr;
-    uint32_t *slot_src = nullptr, *order = nullptr, *map = nullptr;
+    uint2 *cell_rank = nullptr, *slot = nullptr;
+    uint32_t *order = nullptr, *map = nullptr;
+    uint32_t *inverse = nullptr;          // sorted row of each pre-sort row (slab mode)
+    uint32_t *halo_rows[2] = {nullptr, nullptr};  // pre-sort rows packed into each halo message
+    uint64_t halo_n[2] = {0, 0};
+    uint64_t ghost_first[2] = {0, 0}, ghost_n[2] = {0, 0};  // appended ghost batches (pre-sort rows)
+    uint64_t n_ghost = 0;                 // ghost rows among the n rows
+    bool slab_mode = false;
+    unsigned long long *slab_counts = nullptr;  // SLAB_MAX_RANKS counters + cursors
     uint32_t *cells = nullptr;
     uint32_t max_cells = 0;
     uint32_t *h16_cells = nullptr;  // 65536 + 2 counters for the hash16 ordering
@@ -178,8 +186,9 @@ int compute_bbox(sph_handle *h)
 }
 
 // Neighbour-search build for the current positions: plan -> zero -> histogram -> scan -> place
-// -> stable order -> gather. Flips pos/vel buffers; afterwards rows are in cell order and
-// h->cells holds the cell start offsets.
+// -> canonical order -> gather. Flips pos/vel buffers; afterwards rows are in cell order and
+// h->cells holds the cell start offsets. Dropped rows (slab mode) do not survive the build, so
+// h->n shrinks to the surviving row count.
 int build_grid(sph_handle *h)
 {
     const uint32_t n = (uint32_t)h->n;
@@ -195,16 +204,25 @@ int build_grid(sph_handle *h)
     k_scan_exclusive<<<h->num_sms * 4, SCAN_THREADS, 0, s>>>(h->cells, &h->gd->ncells, h->tile_state,
                                                             &h->ctr->ticket, h->epoch);
     CK_LAUNCH();
-    k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, n, h->cells, h->slot_src);
+    k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot);
     CK_LAUNCH();
-    k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot_src, h->cell_rank, n, h->cells,
-                                                                      h->order);
-    CK_LAUNCH();
-    k_gather_sorted<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->order, n, h->P.h, h->pos[h->cur],
-                                                                       h->vel[h->cur], h->pos[h->cur ^ 1],
-                                                                       h->vel[h->cur ^ 1]);
-    CK_LAUNCH();
+    uint32_t n_sorted = n;
+    if (h->slab_mode) {
+        k_publish_rows<<<1, 32, 0, s>>>(h->cells, h->gd, h->ctr);
+        CK_LAUNCH();
+        CK(cudaMemcpyAsync(&n_sorted, &h->ctr->aux[2], sizeof n_sorted, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    if (n_sorted) {
+        k_stable_order<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
+            h->slot, h->cell_rank, n_sorted, h->cells, h->order, h->slab_mode ? h->inverse : nullptr);
+        CK_LAUNCH();
+        k_gather_sorted<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
+            h->order, n_sorted, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1], h->vel[h->cur ^ 1]);
+        CK_LAUNCH();
+    }
     h->cur ^= 1;
+    h->n = n_sorted;
     return SPH_OK;
 }
 
@@ -255,7 +273,7 @@ int build_hash16_order(sph_handle *h, bool need_map)
     CK(cudaMemsetAsync(h->h16_cells, 0, sizeof(uint32_t) * 65540, s));
     CK(cudaMemsetAsync(&h->ctr->aux[0], 0, sizeof(uint32_t), s));
     if (n) {
-        k_hash16_hist<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->pos[h->cur], n, h->h16_cells,
+        k_hash16_hist<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->vel[h->cur], n, h->h16_cells,
                                                                      need_map ? h->cell_rank : nullptr);
         CK_LAUNCH();
     }
@@ -264,10 +282,11 @@ int build_hash16_order(sph_handle *h, bool need_map)
                                                 h->epoch);
     CK_LAUNCH();
     if (need_map && n) {
-        k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, n, h->h16_cells, h->slot_src);
+        k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->h16_cells,
+                                                                   h->slot);
         CK_LAUNCH();
-        k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot_src, h->cell_rank, n,
-                                                                          h->h16_cells, h->map);
+        k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot, h->cell_rank, n, h->h16_cells,
+                                                                          h->map, nullptr);
         CK_LAUNCH();
     }
     return SPH_OK;
@@ -279,6 +298,8 @@ int after_upload(sph_handle *h, uint64_t n)
     h->steps = 0;
     h->have_state = true;
     h->have_step = false;
+    h->n_ghost = 0;
+    h->ghost_n[0] = h->ghost_n[1] = h->halo_n[0] = h->halo_n[1] = 0;
     return compute_bbox(h);
 }
 
@@ -379,7 +400,11 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaMalloc(&nh->nlist, sizeof(uint32_t) * cap * NLIST_ROWS));
     CKC(cudaMalloc(&nh->ncount, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->cell_rank, sizeof(uint2) * cap));
-    CKC(cudaMalloc(&nh->slot_src, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->slot, sizeof(uint2) * cap));
+    CKC(cudaMalloc(&nh->inverse, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->halo_rows[0], sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->halo_rows[1], sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->slab_counts, sizeof(unsigned long long) * (2 * SLAB_MAX_RANKS + 8)));
     CKC(cudaMalloc(&nh->order, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->map, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->cells, sizeof(uint32_t) * ((size_t)nh->max_cells + 8)));
@@ -407,7 +432,8 @@ int sph_destroy(sph_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int b = 0; b < 2; ++b) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); }
-    cudaFree(h->force); cudaFree(h->rho); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot_src);
+    cudaFree(h->force); cudaFree(h->rho); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot); cudaFree(h->inverse);
+    cudaFree(h->halo_rows[0]); cudaFree(h->halo_rows[1]); cudaFree(h->slab_counts);
     cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
     cudaFree(h->stats_acc); cudaFree(h->scratch);
@@ -512,7 +538,7 @@ int sph_download(sph_handle *h, int order, float *host_pos, float *host_vel, flo
     const uint32_t *map = nullptr;
     if (order == SPH_ORDER_ID) {
         CK(cudaMemsetAsync(&h->ctr->aux[1], 0, sizeof(uint32_t), h->stream));
-        k_rows_by_id<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->vel[h->cur], (uint32_t)n, h->map,
+        k_rows_by_id<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)n, h->map,
                                                                             &h->ctr->aux[1]);
         CK_LAUNCH();
         uint32_t bad = 0;
@@ -697,7 +723,7 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
     k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)n, h->gd, h->cells, h->P,
                                                                          h->rho, h->nlist, h->ncount, (uint32_t)h->cap);
     CK_LAUNCH();
-    uint32_t *dcounts = h->slot_src;  // free after build_grid
+    uint32_t *dcounts = reinterpret_cast<uint32_t *>(h->slot);  // free after build_grid
     k_neighbor_lists<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)n,
                                                                                 h->gd, h->cells, h->P, h->nlist, h->ncount,
                                                                                 (uint32_t)h->cap, dcounts, nullptr, nullptr);
@@ -744,7 +770,7 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     if (rc) return rc;
     if (!out) return fail(h, SPH_ERR_INVALID, "out is NULL");
     std::memset(out, 0, sizeof *out);
-    out->count = h->n;
+    out->count = h->n - h->n_ghost;
     out->steps = h->steps;
     if (!h->have_state || h->n == 0) return SPH_OK;
     GridDesc g{};
@@ -764,7 +790,7 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     out->grid_cells = g.ncells;
     out->clamped = c.clamped;
     out->nan_count = a.nan_count;
-    out->mean_density = a.sum_rho / (double)h->n;
+    out->mean_density = a.sum_rho / (double)(h->n - h->n_ghost ? h->n - h->n_ghost : 1);
     float mx;
     std::memcpy(&mx, &a.max_rho_bits, 4);
     out->max_density = mx;
@@ -831,6 +857,219 @@ int sph_selftest_division(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mi
     CK(cudaMemcpyAsync(&bad, dout, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *mismatches_out = bad;
+    return SPH_OK;
+}
+
+// ---- slab decomposition ---------------------------------------------------------------------------
+
+namespace {
+int make_cuts(sph_handle *h, const int32_t *cuts, int world, SlabCuts &c)
+{
+    if (!cuts || world < 1 || world > SLAB_MAX_RANKS)
+        return fail(h, SPH_ERR_INVALID, "world must be in [1, %d] and cuts non-NULL", SLAB_MAX_RANKS);
+    c.world = world;
+    for (int k = 0; k <= world; ++k) c.lo[k] = cuts[k];
+    for (int k = 1; k < world; ++k)
+        if (cuts[k] > cuts[k + 1] && k + 1 < world)
+            return fail(h, SPH_ERR_INVALID, "cuts must be non-decreasing");
+    return SPH_OK;
+}
+}  // namespace
+
+int sph_slab_enable(sph_handle *h, int enable)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    h->slab_mode = enable != 0;
+    return SPH_OK;
+}
+
+uint64_t sph_slab_owned(const sph_handle *h) { return h ? h->n - h->n_ghost : 0; }
+
+int sph_slab_count(sph_handle *h, const int32_t *cuts, int world, uint64_t *host_counts)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!host_counts) return fail(h, SPH_ERR_INVALID, "counts is NULL");
+    SlabCuts c;
+    rc = make_cuts(h, cuts, world, c);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->slab_counts, 0, sizeof(unsigned long long) * SLAB_MAX_RANKS, h->stream));
+    if (h->n) {
+        k_slab_count<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)h->n, h->P.h, c,
+                                                                                   h->slab_counts);
+        CK_LAUNCH();
+    }
+    unsigned long long tmp[SLAB_MAX_RANKS];
+    CK(cudaMemcpyAsync(tmp, h->slab_counts, sizeof(unsigned long long) * world, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < world; ++k) host_counts[k] = tmp[k];
+    return SPH_OK;
+}
+
+int sph_slab_pack(sph_handle *h, const int32_t *cuts, int world, int self, void *dev_buf, const uint64_t *row_offsets)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (self < 0 || self >= world || !row_offsets) return fail(h, SPH_ERR_INVALID, "bad self / offsets");
+    SlabCuts c;
+    rc = make_cuts(h, cuts, world, c);
+    if (rc) return rc;
+    SlabOffsets off{};
+    for (int k = 0; k < world; ++k) off.row[k] = row_offsets[k];
+    unsigned long long *cursors = h->slab_counts + SLAB_MAX_RANKS;
+    CK(cudaMemsetAsync(cursors, 0, sizeof(unsigned long long) * SLAB_MAX_RANKS, h->stream));
+    if (h->n) {
+        k_slab_pack<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, c, self, off, cursors, (float4 *)dev_buf);
+        CK_LAUNCH();
+    }
+    h->n_ghost = 0;  // last step's ghosts are dropped rows now
+    h->ghost_n[0] = h->ghost_n[1] = 0;
+    h->have_step = false;
+    return SPH_OK;
+}
+
+int sph_slab_append(sph_handle *h, const void *dev_rows, uint64_t nrows, int kind)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (kind < 0 || kind > 2) return fail(h, SPH_ERR_INVALID, "kind must be 0 (owned), 1 or 2 (ghost batch)");
+    if (h->n + nrows > h->cap)
+        return fail(h, SPH_ERR_CAPACITY, "append of %llu rows to %llu exceeds capacity %llu", (unsigned long long)nrows,
+                    (unsigned long long)h->n, (unsigned long long)h->cap);
+    if (nrows) {
+        if (!dev_rows) return fail(h, SPH_ERR_INVALID, "rows is NULL");
+        k_slab_append<<<blocks_for(nrows, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            (const float4 *)dev_rows, (uint32_t)nrows, (uint32_t)h->n, kind != 0, h->pos[h->cur], h->vel[h->cur]);
+        CK_LAUNCH();
+    }
+    if (kind) {
+        h->ghost_first[kind - 1] = h->n;
+        h->ghost_n[kind - 1] = nrows;
+        h->n_ghost += nrows;
+    }
+    h->n += nrows;
+    h->have_state = true;
+    h->have_step = false;
+    return SPH_OK;
+}
+
+int sph_slab_pack_halo(sph_handle *h, int32_t cell_x, int side, void *dev_buf, uint64_t capacity_rows, uint64_t *nrows_out)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (side < 0 || side > 1 || !nrows_out) return fail(h, SPH_ERR_INVALID, "bad side / nrows_out");
+    unsigned long long *cursor = h->slab_counts + 2 * SLAB_MAX_RANKS + side;
+    CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), h->stream));
+    if (h->n) {
+        k_slab_pack_halo<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, cell_x, cursor,
+            (uint32_t)(capacity_rows > h->cap ? h->cap : capacity_rows), (float4 *)dev_buf, h->halo_rows[side]);
+        CK_LAUNCH();
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, cursor, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (cnt > capacity_rows || cnt > h->cap)
+        return fail(h, SPH_ERR_CAPACITY, "halo layer has %llu rows, buffer holds %llu", cnt, (unsigned long long)capacity_rows);
+    h->halo_n[side] = cnt;
+    *nrows_out = cnt;
+    return SPH_OK;
+}
+
+int sph_slab_step_density(sph_handle *h)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!h->slab_mode) return fail(h, SPH_ERR_STATE, "call sph_slab_enable(h, 1) first");
+    if (h->n == 0) return SPH_OK;
+    rc = compute_bbox(h);  // arrivals and new ghosts are not covered by the integration's box
+    if (rc) return rc;
+    rc = build_grid(h);
+    if (rc) return rc;
+    const uint32_t n = (uint32_t)h->n;
+    if (n) {
+        k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], n, h->gd, h->cells, h->P,
+                                                                             h->rho, h->nlist, h->ncount, (uint32_t)h->cap);
+        CK_LAUNCH();
+    }
+    h->launches += 10;
+    return SPH_OK;
+}
+
+int sph_slab_pack_halo_density(sph_handle *h, int side, void *dev_buf)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (side < 0 || side > 1) return fail(h, SPH_ERR_INVALID, "bad side");
+    const uint64_t n = h->halo_n[side];
+    if (n) {
+        if (!dev_buf) return fail(h, SPH_ERR_INVALID, "buffer is NULL");
+        k_slab_pack_density<<<blocks_for(n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(h->rho, h->inverse, h->halo_rows[side],
+                                                                                       (uint32_t)n, (float *)dev_buf);
+        CK_LAUNCH();
+    }
+    return SPH_OK;
+}
+
+int sph_slab_set_ghost_density(sph_handle *h, int side, const void *dev_buf, uint64_t nrows)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (side < 0 || side > 1) return fail(h, SPH_ERR_INVALID, "bad side");
+    if (nrows != h->ghost_n[side])
+        return fail(h, SPH_ERR_INVALID, "ghost batch %d has %llu rows, got %llu densities", side,
+                    (unsigned long long)h->ghost_n[side], (unsigned long long)nrows);
+    if (nrows) {
+        k_slab_set_ghost_density<<<blocks_for(nrows, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            h->rho, h->inverse, (uint32_t)h->ghost_first[side], (uint32_t)nrows, (const float *)dev_buf);
+        CK_LAUNCH();
+    }
+    return SPH_OK;
+}
+
+int sph_slab_step_forces(sph_handle *h, float dt)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!(dt > 0.f)) dt = h->settings.dt;
+    const uint32_t n = (uint32_t)h->n;
+    if (n) {
+        cudaStream_t s = h->stream;
+        k_forces<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->rho, n, h->gd, h->cells,
+                                                                    h->P, h->nlist, h->ncount, (uint32_t)h->cap, h->force);
+        CK_LAUNCH();
+        k_integrate<<<blocks_for(n, 256), 256, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho, n, h->P, dt, h->ctr,
+                                                      h->parity ^ 1);
+        CK_LAUNCH();
+    }
+    h->launches += 2;
+    ++h->steps;
+    h->have_step = true;
+    return SPH_OK;
+}
+
+int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, uint64_t *host_hist)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!host_hist || nbins == 0 || nbins > (1u << 24)) return fail(h, SPH_ERR_INVALID, "bad histogram arguments");
+    rc = ensure_scratch(h, sizeof(unsigned long long) * nbins + 256);
+    if (rc) return rc;
+    unsigned long long *d = (unsigned long long *)h->scratch;
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * nbins, h->stream));
+    if (h->n) {
+        k_slab_xhist<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)h->n, h->P.h,
+                                                                                   x_cell_lo, nbins, d);
+        CK_LAUNCH();
+    }
+    CK(cudaMemcpyAsync(host_hist, d, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return SPH_OK;
 }
 

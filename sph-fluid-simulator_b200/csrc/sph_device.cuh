@@ -13,13 +13,17 @@
 namespace sphb {
 
 // ---- pos.w / vel.w bit lanes --------------------------------------------------------------
-// pos.w carries, as raw bits: [15:0] hash16 of the particle's start-of-step cell,
-// bit 16 "the 27 neighbour-cell hashes of this cell are not all distinct" (the reference then
-// visits some bucket more than once, src/sph.cpp:40-65), bit 17 "ghost" (slab halo copy).
-// vel.w carries the particle id as raw bits.
+// pos.w carries, as raw bits, the particle's identity: [30:0] id, bit 31 "ghost" (a slab halo copy
+// owned by another rank: takes part in neighbour sums as j only, is never integrated). The value
+// 0xFFFFFFFF marks a dropped row (a migrated particle or last step's ghost) that the next grid
+// build skips, which is how rows leave the arrays.
+// vel.w carries the hash16 of the particle's start-of-step cell (what Particle::hash holds after
+// the reference step), for read-out and for the hash-table parity artefact.
+constexpr uint32_t W_ID_MASK = 0x7FFFFFFFu;
+constexpr uint32_t W_GHOST = 0x80000000u;
+constexpr uint32_t W_DROP = 0xFFFFFFFFu;
 constexpr uint32_t W_HASH_MASK = 0xFFFFu;
-constexpr uint32_t W_DUP = 1u << 16;
-constexpr uint32_t W_GHOST = 1u << 17;
+constexpr uint32_t CELL_NONE = 0xFFFFFFFFu;  // cell_rank.x of a dropped row
 
 // Multipliers of getHash (reference src/neighborTable.cpp:8-10).
 constexpr uint32_t HASH_MX = 73856093u, HASH_MY = 19349663u, HASH_MZ = 83492791u;

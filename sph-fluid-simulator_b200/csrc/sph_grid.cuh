@@ -79,10 +79,11 @@ __global__ void __launch_bounds__(GRID_THREADS)
 k_bbox(const float4 *__restrict__ pos, uint32_t n, float h, StepCounters *ctr, int parity)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
+    bool valid = i < n;
     int cx = 0, cy = 0, cz = 0;
     if (valid) {
         const float4 p = pos[i];
+        valid = __float_as_uint(p.w) != W_DROP;
         cx = cell_of(p.x, h); cy = cell_of(p.y, h); cz = cell_of(p.z, h);
     }
     bbox_accumulate_block(ctr->bbox[parity], cx, cy, cz, valid);
@@ -156,6 +157,10 @@ k_cell_hist(const float4 *__restrict__ pos, uint32_t n, float h, const GridDesc 
     if (i >= n) return;
     const GridDesc g = *gd;
     const float4 p = pos[i];
+    if (__float_as_uint(p.w) == W_DROP) {  // migrated away / stale ghost: leaves the arrays here
+        cell_rank[i] = make_uint2(CELL_NONE, 0u);
+        return;
+    }
     bool clamped;
     const uint32_t c = grid_index(g, cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h), clamped);
     const uint32_t r = atomicAdd(&counts[c], 1u);
@@ -262,51 +267,60 @@ k_scan_exclusive(uint32_t *__restrict__ data, const uint32_t *__restrict__ n_ptr
 
 // ---- placement and stable order -------------------------------------------------------------
 
-// slot[start[cell] + rank] = source row. Within a cell the rank came from atomicAdd, so the
-// order inside a cell segment is arbitrary at this point.
+// slot[start[cell] + rank] = (source row, particle id). Within a cell the rank came from
+// atomicAdd, so the order inside a cell segment is arbitrary at this point.
 __global__ void __launch_bounds__(GRID_THREADS)
-k_place(const uint2 *__restrict__ cell_rank, uint32_t n, const uint32_t *__restrict__ starts,
-        uint32_t *__restrict__ slot_src)
+k_place(const uint2 *__restrict__ cell_rank, const float4 *__restrict__ pos, uint32_t n,
+        const uint32_t *__restrict__ starts, uint2 *__restrict__ slot)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint2 cr = cell_rank[i];
-    slot_src[starts[cr.x] + cr.y] = i;
+    if (cr.x == CELL_NONE) return;
+    slot[starts[cr.x] + cr.y] = make_uint2(i, __float_as_uint(pos[i].w) & W_ID_MASK);
 }
 
-// Make the order inside every cell segment ascending in source row (== a stable counting sort,
-// hence deterministic run to run): each slot counts the smaller entries of its own segment.
+// Canonical order inside every cell segment: ascending particle id (ids are unique). Each slot
+// counts the smaller ids of its own segment. Because the order depends on nothing but the ids,
+// sums over a cell do not depend on how rows were laid out before the sort — run to run, and
+// between a single-GPU run and a slab-decomposed one. inverse (optional) = sorted row of each
+// source row.
 __global__ void __launch_bounds__(GRID_THREADS)
-k_stable_order(const uint32_t *__restrict__ slot_src, const uint2 *__restrict__ cell_rank, uint32_t n,
-               const uint32_t *__restrict__ starts, uint32_t *__restrict__ order)
+k_stable_order(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_rank, uint32_t n_sorted,
+               const uint32_t *__restrict__ starts, uint32_t *__restrict__ order, uint32_t *__restrict__ inverse)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n) return;
-    const uint32_t src = slot_src[d];
-    const uint32_t c = cell_rank[src].x;
+    if (d >= n_sorted) return;
+    const uint2 me = slot[d];
+    const uint32_t c = cell_rank[me.x].x;
     const uint32_t s = starts[c], e = starts[c + 1];
     uint32_t k = 0;
-    for (uint32_t t = s; t < e; ++t) k += (slot_src[t] < src);
-    order[s + k] = src;
+    for (uint32_t t = s; t < e; ++t) k += (slot[t].y < me.y);
+    order[s + k] = me.x;
+    if (inverse) inverse[me.x] = s + k;
 }
 
-// Gather rows into cell order; attach hash16 + duplicate flag to pos.w (vel.w keeps the id).
+// Gather rows into cell order. pos.w (identity) rides along; vel.w becomes the hash16 of the
+// start-of-step cell.
 __global__ void __launch_bounds__(GRID_THREADS)
-k_gather_sorted(const uint32_t *__restrict__ order, uint32_t n, float h,
+k_gather_sorted(const uint32_t *__restrict__ order, uint32_t n_sorted, float h,
                 const float4 *__restrict__ pos_in, const float4 *__restrict__ vel_in,
                 float4 *__restrict__ pos_out, float4 *__restrict__ vel_out)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n) return;
+    if (d >= n_sorted) return;
     const uint32_t src = order[d];
-    float4 p = pos_in[src];
-    const float4 v = vel_in[src];
-    const int cx = cell_of(p.x, h), cy = cell_of(p.y, h), cz = cell_of(p.z, h);
-    uint32_t w = hash16_of(cx, cy, cz) | (__float_as_uint(p.w) & W_GHOST);
-    if (nbhd_has_duplicate_hash(cx, cy, cz)) w |= W_DUP;
-    p.w = __uint_as_float(w);
+    const float4 p = pos_in[src];
+    float4 v = vel_in[src];
+    v.w = __uint_as_float(hash16_of(cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h)));
     pos_out[d] = p;
     vel_out[d] = v;
+}
+
+// Rows that survived the build (= the scan's end sentinel), published for the host.
+__global__ void k_publish_rows(const uint32_t *__restrict__ starts, const GridDesc *__restrict__ gd, StepCounters *ctr)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) ctr->aux[2] = starts[gd->ncells];
 }
 
 }  // namespace sphb

@@ -9,15 +9,15 @@ namespace sphb {
 
 constexpr int IO_THREADS = 256;
 
-// xyz triples (+ optional ids) -> float4 rows. pos.w = 0 (flags), vel.w = id bits.
+// xyz triples (+ optional ids) -> float4 rows. pos.w = id bits, vel.w = 0 (hash16 lane).
 __global__ void __launch_bounds__(IO_THREADS)
 k_import_xyz(const float *__restrict__ pos3, const float *__restrict__ vel3, const uint32_t *__restrict__ ids,
              uint32_t n, float4 *__restrict__ pos, float4 *__restrict__ vel)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    pos[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], 0.f);
-    vel[i] = make_float4(vel3[3 * i], vel3[3 * i + 1], vel3[3 * i + 2], __uint_as_float(ids ? ids[i] : i));
+    pos[i] = make_float4(pos3[3 * i], pos3[3 * i + 1], pos3[3 * i + 2], __uint_as_float((ids ? ids[i] : i) & W_ID_MASK));
+    vel[i] = make_float4(vel3[3 * i], vel3[3 * i + 1], vel3[3 * i + 2], 0.f);
 }
 
 __global__ void __launch_bounds__(IO_THREADS)
@@ -27,19 +27,19 @@ k_import_xyzw(const float4 *__restrict__ pos_in, const float4 *__restrict__ vel_
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pos_in[i], v = vel_in[i];
-    p.w = 0.f;
-    v.w = __uint_as_float(i);
+    p.w = __uint_as_float(i);
+    v.w = 0.f;
     pos[i] = p;
     vel[i] = v;
 }
 
 // row_of_dest[id(row)] = row, for SPH_ORDER_ID exports.
 __global__ void __launch_bounds__(IO_THREADS)
-k_rows_by_id(const float4 *__restrict__ vel, uint32_t n, uint32_t *__restrict__ row_of_dest, uint32_t *bad)
+k_rows_by_id(const float4 *__restrict__ pos, uint32_t n, uint32_t *__restrict__ row_of_dest, uint32_t *bad)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t id = __float_as_uint(vel[i].w);
+    const uint32_t id = __float_as_uint(pos[i].w);  // a ghost bit makes the id out of range on purpose
     if (id < n) row_of_dest[id] = i;
     else atomicAdd(bad, 1u);
 }
@@ -69,8 +69,8 @@ k_export(const float4 *__restrict__ pos, const float4 *__restrict__ vel, const f
     }
     if (out.density) out.density[d] = rho[r];
     if (out.pressure) out.pressure[d] = __fmul_rn(P.gas_constant, __fsub_rn(rho[r], P.rest_density));
-    if (out.hash16) out.hash16[d] = (uint16_t)(__float_as_uint(p.w) & W_HASH_MASK);
-    if (out.id) out.id[d] = __float_as_uint(v.w);
+    if (out.hash16) out.hash16[d] = (uint16_t)(__float_as_uint(v.w) & W_HASH_MASK);
+    if (out.id) out.id[d] = __float_as_uint(p.w);  // bit 31 set = ghost row (slab mode)
 }
 
 // Renderer read-out: float4 (x, y, z, 1).
@@ -110,8 +110,8 @@ k_import_aos(const uint32_t *__restrict__ aos, uint32_t n, float4 *__restrict__ 
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t *r = aos + (size_t)AOS_WORDS * i;
-    pos[i] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), 0.f);
-    vel[i] = make_float4(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(i));
+    pos[i] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(i));
+    vel[i] = make_float4(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]), 0.f);
 }
 
 // Output row d = device row map[d]; the dead acceleration words come from the caller's input row
@@ -126,7 +126,7 @@ k_export_aos(const float4 *__restrict__ pos, const float4 *__restrict__ vel, con
     const uint32_t r = map ? map[d] : d;
     const float4 p = pos[r], v = vel[r], f = force[r];
     const float rh = rho[r];
-    const uint32_t id = __float_as_uint(v.w);
+    const uint32_t id = __float_as_uint(p.w) & W_ID_MASK;
     const uint32_t *in = aos_in + (size_t)AOS_WORDS * id;
     uint32_t *o = aos_out + (size_t)AOS_WORDS * d;
     o[0] = __float_as_uint(p.x); o[1] = __float_as_uint(p.y); o[2] = __float_as_uint(p.z);
@@ -135,18 +135,18 @@ k_export_aos(const float4 *__restrict__ pos, const float4 *__restrict__ vel, con
     o[9] = __float_as_uint(f.x); o[10] = __float_as_uint(f.y); o[11] = __float_as_uint(f.z);
     o[12] = __float_as_uint(rh);
     o[13] = __float_as_uint(__fmul_rn(P.gas_constant, __fsub_rn(rh, P.rest_density)));
-    o[14] = __float_as_uint(p.w) & W_HASH_MASK;
+    o[14] = __float_as_uint(v.w) & W_HASH_MASK;
 }
 
 // ---- hash16 ordering (order class of the reference's std::sort) and table ----------------------
 
 __global__ void __launch_bounds__(IO_THREADS)
-k_hash16_hist(const float4 *__restrict__ pos, uint32_t n, uint32_t *__restrict__ counts,
+k_hash16_hist(const float4 *__restrict__ vel, uint32_t n, uint32_t *__restrict__ counts,
               uint2 *__restrict__ key_rank)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t k = __float_as_uint(pos[i].w) & W_HASH_MASK;
+    const uint32_t k = __float_as_uint(vel[i].w) & W_HASH_MASK;
     const uint32_t r = atomicAdd(&counts[k], 1u);
     if (key_rank) key_rank[i] = make_uint2(k, r);
 }
@@ -181,6 +181,7 @@ k_stats(const float4 *__restrict__ pos, const float4 *__restrict__ vel, const fl
     float mx = 0.f;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pos[i], v = vel[i];
+        if (__float_as_uint(p.w) & W_GHOST) continue;  // ghost or dropped row
         const float r = rho[i];
         if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) ++nn;
         sr += (double)r;

@@ -1,0 +1,155 @@
+// Slab decomposition primitives (one process per GPU; the exchange itself is done by the caller
+// with NCCL, see sph-fluid-simulator_b200/slab.py). The domain is cut along x at cell
+// boundaries: rank r owns the particles whose cell.x (reference getCell, src/neighborTable.cpp:
+// 14-17) lies in [cuts[r], cuts[r+1]). The reference has no multi-GPU path; this is new work
+//  and is validated against the single-GPU path and the oracle by particle id.
+//
+// Wire format of a particle row: two float4 — (x, y, z, id bits) and (vx, vy, vz, 0) — 32 bytes.
+#pragma once
+
+#include "sph_device.cuh"
+
+namespace sphb {
+
+constexpr int SLAB_THREADS = 256;
+constexpr int SLAB_MAX_RANKS = 64;
+
+struct SlabCuts {
+    int world;
+    int lo[SLAB_MAX_RANKS + 1];  // lo[0] is treated as -inf, lo[world] as +inf
+};
+
+__device__ __forceinline__ int slab_owner(const SlabCuts &c, int cx)
+{
+    int r = 0;
+    for (int k = 1; k < c.world; ++k) r += (cx >= c.lo[k]);
+    return r;
+}
+
+// counts[r] += live owned rows (not dropped, not ghost) whose owner is rank r.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_count(const float4 *__restrict__ pos, uint32_t n, float h, const SlabCuts cuts,
+             unsigned long long *__restrict__ counts)
+{
+    __shared__ unsigned int s_cnt[SLAB_MAX_RANKS];
+    for (int k = threadIdx.x; k < SLAB_MAX_RANKS; k += blockDim.x) s_cnt[k] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float4 p = pos[i];
+        const uint32_t w = __float_as_uint(p.w);
+        if (w != W_DROP && !(w & W_GHOST)) atomicAdd(&s_cnt[slab_owner(cuts, cell_of(p.x, h))], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < cuts.world; k += blockDim.x)
+        if (s_cnt[k]) atomicAdd(&counts[k], (unsigned long long)s_cnt[k]);
+}
+
+// Rows owned by another rank are copied to that rank's segment of the send buffer and dropped
+// here; last step's ghosts are dropped. cursors[r] must start at 0; offsets[r] is the first row
+// of rank r's segment. The order inside a segment is arbitrary — nothing downstream depends on
+// row order (cells are ordered by particle id).
+struct SlabOffsets {
+    unsigned long long row[SLAB_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_pack(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, const SlabCuts cuts,
+            int self, const SlabOffsets offsets, unsigned long long *__restrict__ cursors,
+            float4 *__restrict__ sendbuf)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    const uint32_t w = __float_as_uint(p.w);
+    if (w == W_DROP) return;
+    bool drop = (w & W_GHOST) != 0u;
+    if (!drop) {
+        const int dest = slab_owner(cuts, cell_of(p.x, h));
+        if (dest != self) {
+            const unsigned long long k = offsets.row[dest] + atomicAdd(&cursors[dest], 1ull);
+            float4 v = vel[i];
+            v.w = 0.f;
+            sendbuf[2 * k] = p;
+            sendbuf[2 * k + 1] = v;
+            drop = true;
+        }
+    }
+    if (drop) {
+        p.w = __uint_as_float(W_DROP);
+        pos[i] = p;
+    }
+}
+
+// Append received rows after the current rows, as owned particles or as ghosts.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_append(const float4 *__restrict__ rows, uint32_t nrows, uint32_t first, bool ghost,
+              float4 *__restrict__ pos, float4 *__restrict__ vel)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nrows) return;
+    float4 p = rows[2 * k];
+    const float4 v = rows[2 * k + 1];
+    uint32_t w = __float_as_uint(p.w) & W_ID_MASK;
+    if (ghost) w |= W_GHOST;
+    p.w = __uint_as_float(w);
+    pos[first + k] = p;
+    vel[first + k] = v;
+}
+
+// Copy the live owned rows of x-cell `cell_x` (a boundary layer of the slab) into a halo
+// message and remember which rows they were, so their densities can follow in the same order.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_pack_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int cell_x,
+                 unsigned long long *__restrict__ cursor, uint32_t capacity, float4 *__restrict__ buf,
+                 uint32_t *__restrict__ rows_out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    const uint32_t w = __float_as_uint(p.w);
+    if (w == W_DROP || (w & W_GHOST) || cell_of(p.x, h) != cell_x) return;
+    const unsigned long long k = atomicAdd(cursor, 1ull);
+    if (k >= capacity) return;  // caller checks the cursor against the capacity
+    float4 v = vel[i];
+    v.w = 0.f;
+    buf[2 * k] = p;
+    buf[2 * k + 1] = v;
+    rows_out[k] = i;
+}
+
+// Densities of the rows a halo message was packed from (pre-sort row -> sorted row via inverse).
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_pack_density(const float *__restrict__ rho, const uint32_t *__restrict__ inverse,
+                    const uint32_t *__restrict__ rows, uint32_t nrows, float *__restrict__ out)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nrows) out[k] = rho[inverse[rows[k]]];
+}
+
+// Densities for a batch of ghost rows that was appended at pre-sort rows [first, first + nrows).
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_set_ghost_density(float *__restrict__ rho, const uint32_t *__restrict__ inverse, uint32_t first,
+                         uint32_t nrows, const float *__restrict__ in)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nrows) rho[inverse[first + k]] = in[k];
+}
+
+// Histogram of cell.x over live owned rows, bins [x_lo, x_lo + nbins) with clamping at both ends
+// (used to choose balanced cuts).
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_xhist(const float4 *__restrict__ pos, uint32_t n, float h, int x_lo, uint32_t nbins,
+             unsigned long long *__restrict__ hist)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    const uint32_t w = __float_as_uint(p.w);
+    if (w == W_DROP || (w & W_GHOST)) return;
+    long long b = (long long)cell_of(p.x, h) - x_lo;
+    b = min(max(b, 0LL), (long long)nbins - 1);
+    atomicAdd(&hist[b], 1ull);
+}
+
+}  // namespace sphb

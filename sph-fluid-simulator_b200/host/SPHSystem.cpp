@@ -87,6 +87,28 @@ void sceneBlock(size_t nx, size_t ny, size_t nz, float sep, float x0, float y0, 
             }
 }
 
+void sceneBlockSlice(size_t nx, size_t ny, size_t nz, float sep, float x0, float y0, float z0, float h,
+                     unsigned seed, size_t i0, size_t i1, float *pos, float *vel, uint32_t *ids)
+{
+    // The same lattice, jitter stream and ids as sceneBlock, but only the rows with i in [i0, i1)
+    // are stored (one x-range of the lattice per rank). rand() is consumed for the others too so
+    // that every rank draws the same jitter for the same particle.
+    std::srand(seed);
+    const size_t w = i1 - i0;
+    for (size_t i = 0; i < nx; i++)
+        for (size_t j = 0; j < ny; j++)
+            for (size_t k = 0; k < nz; k++) {
+                const float rx = jitter(h), ry = jitter(h), rz = jitter(h);
+                if (i < i0 || i >= i1) continue;
+                const size_t row = (i - i0) + (j + ny * k) * w;
+                pos[3 * row + 0] = int(i) * sep + rx + x0;
+                pos[3 * row + 1] = int(j) * sep + ry + y0;
+                pos[3 * row + 2] = int(k) * sep + rz + z0;
+                vel[3 * row + 0] = vel[3 * row + 1] = vel[3 * row + 2] = 0.f;
+                ids[row] = (uint32_t)(i + (j + ny * k) * nx);
+            }
+}
+
 // ---- SPHSystem ----------------------------------------------------------------------------------
 
 SPHSystem::SPHSystem(size_t particleCubeWidth, const SPHSettings &settings, const bool &runOnGPU,
@@ -178,6 +200,16 @@ int sph_scene_block(int nx, int ny, int nz, float sep, float x0, float y0, float
 {
     if (nx < 0 || ny < 0 || nz < 0 || !host_pos_xyz || !host_vel_xyz) return SPH_ERR_INVALID;
     sphb200::sceneBlock((size_t)nx, (size_t)ny, (size_t)nz, sep, x0, y0, z0, h, seed, host_pos_xyz, host_vel_xyz);
+    return SPH_OK;
+}
+
+int sph_scene_block_slice(int nx, int ny, int nz, float sep, float x0, float y0, float z0, float h, unsigned seed,
+                          int i0, int i1, float *host_pos_xyz, float *host_vel_xyz, uint32_t *host_ids)
+{
+    if (nx < 0 || ny < 0 || nz < 0 || i0 < 0 || i1 < i0 || i1 > nx || !host_pos_xyz || !host_vel_xyz || !host_ids)
+        return SPH_ERR_INVALID;
+    sphb200::sceneBlockSlice((size_t)nx, (size_t)ny, (size_t)nz, sep, x0, y0, z0, h, seed, (size_t)i0, (size_t)i1,
+                             host_pos_xyz, host_vel_xyz, host_ids);
     return SPH_OK;
 }
 

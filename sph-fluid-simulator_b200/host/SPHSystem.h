@@ -74,4 +74,9 @@ void sceneCube(size_t width, float h, float *pos_xyz, float *vel_xyz);
 void sceneBlock(size_t nx, size_t ny, size_t nz, float sep, float x0, float y0, float z0, float h,
                 unsigned seed, float *pos_xyz, float *vel_xyz);
 
+/// Rows of sceneBlock with lattice index i in [i0, i1) only, plus their global ids
+/// (id = i + (j + ny*k)*nx); used to seed one rank of a slab-decomposed run.
+void sceneBlockSlice(size_t nx, size_t ny, size_t nz, float sep, float x0, float y0, float z0, float h,
+                     unsigned seed, size_t i0, size_t i1, float *pos_xyz, float *vel_xyz, uint32_t *ids);
+
 }  // namespace sphb200
