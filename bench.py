@@ -305,10 +305,12 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="auto", choices=["auto", "dam-break-1M", "weak"],
+                    help="auto: config 1 at N=1, config 3 (weak scaling, 8 M particles per GPU) at N>1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1 and args.workload != "weak":
         return run_single_gpu(args)
     return run_multi_gpu(args)
 

@@ -37,6 +37,9 @@ typedef void (*gpu_hook_t)(void *particles, void *transforms, size_t n, const vo
                            float dt);
 static gpu_hook_t g_gpu_hook = nullptr;
 
+// With -DREF_HARNESS_EXTERNAL_GPU the symbol comes from the product's drop-in
+// (sph-fluid-simulator_b200/host/updateParticlesGPU_dropin.cpp) linked into the same library.
+#ifndef REF_HARNESS_EXTERNAL_GPU
 void updateParticlesGPU(Particle *particles, glm::mat4 *particleTransforms,
                         const size_t particleCount, const SPHSettings &settings,
                         float deltaTime)
@@ -47,6 +50,7 @@ void updateParticlesGPU(Particle *particles, glm::mat4 *particleTransforms,
     }
     g_gpu_hook(particles, particleTransforms, particleCount, &settings, deltaTime);
 }
+#endif
 
 namespace {
 

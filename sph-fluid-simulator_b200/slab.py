@@ -168,6 +168,10 @@ class SlabDriver:
         self.backend = dist.get_backend(group) if world > 1 else "none"
         self.cuts = [INT_MIN] + [INT_MAX] * world if world == 1 else None
         self.stats = {"migrated_rows": 0, "halo_rows": 0, "steps": 0}
+        # SLAB_PROFILE=1: synchronise after every phase and accumulate wall-clock per phase
+        self.profile = os.environ.get("SLAB_PROFILE") == "1"
+        self.phase_s = {}
+        self._t = None
 
     # -- communication helpers ---------------------------------------------------------------
     def _comm_device(self, t):
@@ -197,6 +201,17 @@ class SlabDriver:
         s = getattr(self.e, "stream", None)
         return torch.cuda.stream(s) if s is not None else _NullCtx()
 
+    def _mark(self, name):
+        if not self.profile:
+            return
+        import time
+        if hasattr(self.e, "sync"):
+            self.e.sync()
+        now = time.perf_counter()
+        if name is not None and self._t is not None:
+            self.phase_s[name] = self.phase_s.get(name, 0.0) + (now - self._t)
+        self._t = now
+
     # -- cuts --------------------------------------------------------------------------------
     def rebalance(self):
         """Recompute balanced cuts from the global cell.x histogram (all ranks get the same cuts)."""
@@ -216,19 +231,24 @@ class SlabDriver:
         if self.cuts is None:
             self.rebalance()
         with self._in_stream():
+            self._mark(None)
             if w > 1:
                 # 1. migration (also drops last step's ghosts)
                 counts = e.count(self.cuts)
+                self._mark("count")
                 counts[r] = 0
                 offsets = np.concatenate([[0], np.cumsum(counts)[:-1]])
                 sendbuf = e.pack(self.cuts, r, offsets, int(counts.sum()))
+                self._mark("pack")
                 arrivals, _ = self._alltoallv(sendbuf, counts.tolist(), ROW_FLOATS)
                 e.append(arrivals, 0)
+                self._mark("migrate_exchange")
                 self.stats["migrated_rows"] += int(counts.sum())
                 # 2. halo: first x-cell of the slab -> left neighbour, last x-cell -> right neighbour
                 cap = e.halo_capacity()
                 left = e.pack_halo(self.cuts[r], 0, cap) if r > 0 else e.empty_rows(0)
                 right = e.pack_halo(self.cuts[r + 1] - 1, 1, cap) if r < w - 1 else e.empty_rows(0)
+                self._mark("pack_halo")
                 hcounts = [0] * w
                 if r > 0:
                     hcounts[r - 1] = left.shape[0]
@@ -239,6 +259,7 @@ class SlabDriver:
                 e.append(ghosts[:n_from_left], 1)
                 e.append(ghosts[n_from_left:], 2)
                 self.stats["halo_rows"] += left.shape[0] + right.shape[0]
+                self._mark("halo_exchange")
             else:
                 # single rank: still go through pack so stale rows are handled uniformly
                 counts = e.count(self.cuts)
@@ -246,6 +267,7 @@ class SlabDriver:
                 hcounts, gcounts, n_from_left = [0], [0], 0
             # 3. density over owned + ghosts
             e.step_density()
+            self._mark("density")
             if w > 1:
                 # 4. densities of the boundary particles follow their positions
                 dl = e.pack_halo_density(0, hcounts[r - 1] if r > 0 else 0)
@@ -253,8 +275,10 @@ class SlabDriver:
                 rho, _ = self._alltoallv(torch.cat([dl, dr]), hcounts, 1)
                 e.set_ghost_density(0, rho[:n_from_left])
                 e.set_ghost_density(1, rho[n_from_left:])
+                self._mark("rho_exchange")
             # 5. forces + integration of the owned particles
             e.step_forces(dt)
+            self._mark("forces")
         self.stats["steps"] += 1
 
 
@@ -370,7 +394,8 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
                              "L2 flushed once before the timed region",
                        "decomposition": "x slabs, all-to-all migration + 1-cell ghost halo + density halo per step (NCCL)",
                        "rank0_mean_density": st.mean_density, "rank0_grid_dim": list(st.grid_dim),
-                       "migrated_rows_rank0": driver.stats["migrated_rows"], "halo_rows_rank0": driver.stats["halo_rows"]},
+                       "migrated_rows_rank0": driver.stats["migrated_rows"], "halo_rows_rank0": driver.stats["halo_rows"],
+                       "phase_ms_per_step_rank0": {k: 1e3 * v / max(driver.stats["steps"], 1) for k, v in driver.phase_s.items()}},
             "clocks": clk,
             "e2e": None,
             "gpu_launches": int(sim.launch_count - launches0),
