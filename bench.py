@@ -34,10 +34,10 @@ sys.path.insert(0, ROOT)
 METRIC = "particle-steps/sec"
 UNIT = "particle-steps/s"
 B_ALG_STEP = 292.0    # algorithmic bytes per particle-step, whole step
-B_ALG_FORCES = 56.0   # forces pass: R pos 16 + vel 16 + (rho, p) 8 + W force 16
+B_ALG_FORCES = 140.0  # forces (R pos 16 + vel 16 + (rho, p) 8 + W force 16) + integration (84), one fused kernel
 B_ALG_DENSITY = 24.0  # density pass: R pos 16 + W (rho, p) 8
 B_ALG_GRID = 128.0    # hash + sort + cell ranges (passes 1-4)
-B_ALG_INTEGRATE = 84.0
+B_ALG_INTEGRATE = 0.0  # fused into the forces kernel
 
 
 def dam_break_1m():
@@ -248,8 +248,8 @@ def run_single_gpu(args):
     # ---- roofline of the dominant kernel (live CUDA-event pass times over the timed region) ----
     peak, peak_src = peaks()
     pass_bytes = {"grid": B_ALG_GRID, "density": B_ALG_DENSITY, "forces": B_ALG_FORCES, "integrate": B_ALG_INTEGRATE}
-    dominant = max(("grid", "density", "forces", "integrate"), key=lambda k: passes[k])
-    dom_name = {"forces": "k_forces", "density": "k_density", "grid": "grid build (7 kernels)", "integrate": "k_integrate"}[dominant]
+    dominant = max(("grid", "density", "forces"), key=lambda k: passes[k])
+    dom_name = {"forces": "k_forces_integrate", "density": "k_density", "grid": "grid build (5 kernels)", "integrate": "-"}[dominant]
     achieved = pass_bytes[dominant] * n / (passes[dominant] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

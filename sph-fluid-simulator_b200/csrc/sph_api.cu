@@ -45,7 +45,7 @@ struct sph_handle {
     float4 *pos[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr};
     int cur = 0;
     float4 *force = nullptr;
-    float *rho = nullptr;
+    uint32_t *hash16 = nullptr;  // start-of-step hash16 of every sorted row (density lives in vel.w)
     uint32_t *nlist = nullptr, *ncount = nullptr;  // neighbour lists written by the density pass
     uint2 *cell_rank = nullptr, *slot = nullptr;
     uint32_t *order = nullptr, *map = nullptr;
@@ -55,6 +55,7 @@ struct sph_handle {
     uint64_t ghost_first[2] = {0, 0}, ghost_n[2] = {0, 0};  // appended ghost batches (pre-sort rows)
     uint64_t n_ghost = 0;                 // ghost rows among the n rows
     bool slab_mode = false;
+    int forces_cfg = 0;
     unsigned long long *slab_counts = nullptr;  // SLAB_MAX_RANKS counters + cursors
     uint32_t *cells = nullptr;
     uint32_t max_cells = 0;
@@ -193,9 +194,7 @@ int build_grid(sph_handle *h)
 {
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
-    k_plan<<<1, 32, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells);
-    CK_LAUNCH();
-    k_zero_cells<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->cells, h->gd);
+    k_plan_zero<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells, h->cells);
     CK_LAUNCH();
     k_cell_hist<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->pos[h->cur], n, h->P.h, h->gd, h->cells,
                                                                    h->cell_rank, h->ctr);
@@ -214,15 +213,35 @@ int build_grid(sph_handle *h)
         CK(cudaStreamSynchronize(s));
     }
     if (n_sorted) {
-        k_stable_order<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
-            h->slot, h->cell_rank, n_sorted, h->cells, h->order, h->slab_mode ? h->inverse : nullptr);
-        CK_LAUNCH();
-        k_gather_sorted<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
-            h->order, n_sorted, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1], h->vel[h->cur ^ 1]);
+        k_order_gather<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
+            h->slot, h->cell_rank, n_sorted, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1],
+            h->vel[h->cur ^ 1], h->hash16, h->slab_mode ? h->inverse : nullptr);
         CK_LAUNCH();
     }
     h->cur ^= 1;
     h->n = n_sorted;
+    return SPH_OK;
+}
+
+// Launch-shape variants of the fused forces+integration kernel (SPH_B200_FORCES_CFG, experiments).
+int launch_forces_integrate(sph_handle *h, uint32_t n, float dt)
+{
+    cudaStream_t s = h->stream;
+#define LAUNCH_FI(T, B)                                                                                          \
+    k_forces_integrate<T, B><<<blocks_for(n, T), T, 0, s>>>(                                                      \
+        h->pos[h->cur], h->vel[h->cur], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap,          \
+        dt, h->pos[h->cur ^ 1], h->vel[h->cur ^ 1], h->force, h->ctr, h->parity ^ 1)
+    switch (h->forces_cfg) {
+    case 1: LAUNCH_FI(128, 8); break;
+    case 2: LAUNCH_FI(128, 10); break;
+    case 3: LAUNCH_FI(64, 16); break;
+    case 4: LAUNCH_FI(256, 4); break;
+    case 5: LAUNCH_FI(128, 12); break;
+    default: LAUNCH_FI(128, 1); break;
+    }
+#undef LAUNCH_FI
+    CK_LAUNCH();
+    h->cur ^= 1;
     return SPH_OK;
 }
 
@@ -244,20 +263,15 @@ int step_once(sph_handle *h, float dt)
     int rc = build_grid(h);
     if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[1], s));
-    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->rho,
-                                                                 h->nlist, h->ncount, (uint32_t)h->cap);
+    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P,
+                                                                 h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap);
     CK_LAUNCH();
     if (timed) CK(cudaEventRecord(ev[2], s));
-    k_forces<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->rho, n, h->gd,
-                                                                h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap,
-                                                                h->force);
-    CK_LAUNCH();
+    rc = launch_forces_integrate(h, n, dt);
+    if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[3], s));
-    k_integrate<<<blocks_for(n, 256), 256, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho, n, h->P, dt,
-                                                  h->ctr, h->parity ^ 1);
-    CK_LAUNCH();
     if (timed) CK(cudaEventRecord(ev[4], s));
-    h->launches += 10;  // plan, zero, hist, scan, place, stable order, gather, density, forces, integrate
+    h->launches += 7;  // plan+zero, hist, scan, place, order+gather, density, forces+integrate
     h->parity ^= 1;
     ++h->steps;
     h->have_step = true;
@@ -273,7 +287,7 @@ int build_hash16_order(sph_handle *h, bool need_map)
     CK(cudaMemsetAsync(h->h16_cells, 0, sizeof(uint32_t) * 65540, s));
     CK(cudaMemsetAsync(&h->ctr->aux[0], 0, sizeof(uint32_t), s));
     if (n) {
-        k_hash16_hist<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->vel[h->cur], n, h->h16_cells,
+        k_hash16_hist<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->hash16, n, h->h16_cells,
                                                                      need_map ? h->cell_rank : nullptr);
         CK_LAUNCH();
     }
@@ -389,6 +403,8 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
         if (v >= 27 && v <= (1ull << 31)) mc = v;
     }
     nh->max_cells = (uint32_t)mc;
+    nh->forces_cfg = 2;  // 128 threads, <= 48 registers: the pass is latency-bound, occupancy wins
+    if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
 
     const size_t cap = (size_t)capacity;
     for (int b = 0; b < 2; ++b) {
@@ -396,7 +412,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
         CKC(cudaMalloc(&nh->vel[b], sizeof(float4) * cap));
     }
     CKC(cudaMalloc(&nh->force, sizeof(float4) * cap));
-    CKC(cudaMalloc(&nh->rho, sizeof(float) * cap));
+    CKC(cudaMalloc(&nh->hash16, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->nlist, sizeof(uint32_t) * cap * NLIST_ROWS));
     CKC(cudaMalloc(&nh->ncount, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->cell_rank, sizeof(uint2) * cap));
@@ -432,7 +448,7 @@ int sph_destroy(sph_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int b = 0; b < 2; ++b) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); }
-    cudaFree(h->force); cudaFree(h->rho); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot); cudaFree(h->inverse);
+    cudaFree(h->force); cudaFree(h->hash16); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot); cudaFree(h->inverse);
     cudaFree(h->halo_rows[0]); cudaFree(h->halo_rows[1]); cudaFree(h->slab_counts);
     cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
@@ -551,7 +567,7 @@ int sph_download(sph_handle *h, int order, float *host_pos, float *host_vel, flo
         if (rc) return rc;
         map = h->map;
     }
-    k_export<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho,
+    k_export<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->hash16,
                                                                     (uint32_t)n, map, h->P, out);
     CK_LAUNCH();
     if (host_pos) CK(cudaMemcpyAsync(host_pos, out.pos3, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
@@ -671,7 +687,7 @@ int sph_update_particles_aos(sph_handle *h, void *host_particles, float *host_ma
     if (rc) return rc;
     rc = build_hash16_order(h, true);
     if (rc) return rc;
-    k_export_aos<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho,
+    k_export_aos<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->hash16,
                                                                 (uint32_t)n, h->map, h->P, aos_in, aos_out);
     CK_LAUNCH();
     CK(cudaMemcpyAsync(host_particles, aos_out, (size_t)60 * n, cudaMemcpyDeviceToHost, s));
@@ -721,7 +737,7 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
     if (rc) return rc;
     // The density pass writes the lists the force pass consumes; report exactly those.
     k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)n, h->gd, h->cells, h->P,
-                                                                         h->rho, h->nlist, h->ncount, (uint32_t)h->cap);
+                                                                         h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap);
     CK_LAUNCH();
     uint32_t *dcounts = reinterpret_cast<uint32_t *>(h->slot);  // free after build_grid
     k_neighbor_lists<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)n,
@@ -734,7 +750,7 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
         if (rc) return rc;
         ExportPtrs out{};
         out.id = (uint32_t *)h->scratch;
-        k_export<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho,
+        k_export<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->hash16,
                                                                         (uint32_t)n, nullptr, h->P, out);
         CK_LAUNCH();
         CK(cudaMemcpyAsync(host_ids_out, out.id, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, h->stream));
@@ -778,7 +794,7 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     StatsAccum a{};
     CK(cudaMemsetAsync(h->stats_acc, 0, sizeof(StatsAccum), h->stream));
     if (h->have_step) {
-        k_stats<<<h->num_sms * 4, IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], h->rho, (uint32_t)h->n, h->stats_acc);
+        k_stats<<<h->num_sms * 4, IO_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->stats_acc);
         CK_LAUNCH();
     }
     CK(cudaMemcpyAsync(&a, h->stats_acc, sizeof a, cudaMemcpyDeviceToHost, h->stream));
@@ -994,10 +1010,10 @@ int sph_slab_step_density(sph_handle *h)
     const uint32_t n = (uint32_t)h->n;
     if (n) {
         k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], n, h->gd, h->cells, h->P,
-                                                                             h->rho, h->nlist, h->ncount, (uint32_t)h->cap);
+                                                                             h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap);
         CK_LAUNCH();
     }
-    h->launches += 10;
+    h->launches += 6;
     return SPH_OK;
 }
 
@@ -1009,7 +1025,7 @@ int sph_slab_pack_halo_density(sph_handle *h, int side, void *dev_buf)
     const uint64_t n = h->halo_n[side];
     if (n) {
         if (!dev_buf) return fail(h, SPH_ERR_INVALID, "buffer is NULL");
-        k_slab_pack_density<<<blocks_for(n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(h->rho, h->inverse, h->halo_rows[side],
+        k_slab_pack_density<<<blocks_for(n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(h->vel[h->cur], h->inverse, h->halo_rows[side],
                                                                                        (uint32_t)n, (float *)dev_buf);
         CK_LAUNCH();
     }
@@ -1026,7 +1042,7 @@ int sph_slab_set_ghost_density(sph_handle *h, int side, const void *dev_buf, uin
                     (unsigned long long)h->ghost_n[side], (unsigned long long)nrows);
     if (nrows) {
         k_slab_set_ghost_density<<<blocks_for(nrows, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
-            h->rho, h->inverse, (uint32_t)h->ghost_first[side], (uint32_t)nrows, (const float *)dev_buf);
+            h->vel[h->cur], h->inverse, (uint32_t)h->ghost_first[side], (uint32_t)nrows, (const float *)dev_buf);
         CK_LAUNCH();
     }
     return SPH_OK;
@@ -1041,14 +1057,10 @@ int sph_slab_step_forces(sph_handle *h, float dt)
     const uint32_t n = (uint32_t)h->n;
     if (n) {
         cudaStream_t s = h->stream;
-        k_forces<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->rho, n, h->gd, h->cells,
-                                                                    h->P, h->nlist, h->ncount, (uint32_t)h->cap, h->force);
-        CK_LAUNCH();
-        k_integrate<<<blocks_for(n, 256), 256, 0, s>>>(h->pos[h->cur], h->vel[h->cur], h->force, h->rho, n, h->P, dt, h->ctr,
-                                                      h->parity ^ 1);
-        CK_LAUNCH();
+        rc = launch_forces_integrate(h, n, dt);
+        if (rc) return rc;
     }
-    h->launches += 2;
+    h->launches += 1;
     ++h->steps;
     h->have_step = true;
     return SPH_OK;

@@ -97,55 +97,67 @@ __global__ void k_reset_bbox(StepCounters *ctr, int parity)
 
 // ---- plan: bounding box -> GridDesc -------------------------------------------------------
 
-// One thread. Reads bbox[parity] (filled by the previous step's integration or by k_bbox after
-// an upload), writes the grid description of this step, re-arms bbox[parity^1] for the
-// integration kernel of this step and resets the per-step counters.
-__global__ void k_plan(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells)
+// Grid description of a step from the bounding box of occupied cells: one padding layer on every
+// side; if the box exceeds the dense-grid allocation the high side of the longest axis is clipped
+// (y first: it is the only unbounded axis) and grid_index() clamps the outliers into the last
+// interior layer.
+__device__ __forceinline__ GridDesc plan_grid(const int *b, uint32_t max_cells)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int *b = ctr->bbox[parity];
     long long lo[3] = {b[0], b[1], b[2]};
     long long dim[3];
     for (int a = 0; a < 3; ++a) {
         long long ext = (long long)b[3 + a] - lo[a] + 1;  // occupied cells on this axis
         if (ext < 1) ext = 1;                              // empty box (n == 0)
-        dim[a] = ext + 2;                                  // one padding layer on both sides
+        dim[a] = ext + 2;
     }
-    // Keep the dense grid within its allocation: clip the high side of the longest axis until
-    // it fits. Clipped particles are clamped into the last interior layer by grid_index().
     while (dim[0] * dim[1] * dim[2] > (long long)max_cells) {
-        int a = 1;  // prefer clipping y (the only unbounded axis: there is no ceiling)
+        int a = 1;
         if (dim[0] > dim[a]) a = 0;
         if (dim[2] > dim[a]) a = 2;
         dim[a] = max(3LL, (dim[a] + 1) / 2);
         if (dim[0] == 3 && dim[1] == 3 && dim[2] == 3) break;
     }
-    gd->ox = (int)max(lo[0] - 1, (long long)(-0x7fffffff - 1));
-    gd->oy = (int)max(lo[1] - 1, (long long)(-0x7fffffff - 1));
-    gd->oz = (int)max(lo[2] - 1, (long long)(-0x7fffffff - 1));
-    gd->nx = (int)dim[0]; gd->ny = (int)dim[1]; gd->nz = (int)dim[2];
-    gd->ncells = (uint32_t)(dim[0] * dim[1] * dim[2]);
-    gd->sz = (uint32_t)dim[1];
-    gd->sx = (uint32_t)(dim[1] * dim[2]);
-    ctr->ticket = 0;
-    ctr->clamped = 0;
-    int *nb = ctr->bbox[parity ^ 1];
-    nb[0] = nb[1] = nb[2] = 0x7fffffff;
-    nb[3] = nb[4] = nb[5] = -0x7fffffff - 1;
+    GridDesc g;
+    g.ox = (int)max(lo[0] - 1, (long long)(-0x7fffffff - 1));
+    g.oy = (int)max(lo[1] - 1, (long long)(-0x7fffffff - 1));
+    g.oz = (int)max(lo[2] - 1, (long long)(-0x7fffffff - 1));
+    g.nx = (int)dim[0]; g.ny = (int)dim[1]; g.nz = (int)dim[2];
+    g.ncells = (uint32_t)(dim[0] * dim[1] * dim[2]);
+    g.sz = (uint32_t)dim[1];
+    g.sx = (uint32_t)(dim[1] * dim[2]);
+    g.pad_ = 0;
+    return g;
 }
 
-// ---- histogram ------------------------------------------------------------------------------
-
-// Zero counts[0 .. ncells] (the extra entry becomes the end sentinel after the scan).
-__global__ void __launch_bounds__(GRID_THREADS) k_zero_cells(uint32_t *__restrict__ counts, const GridDesc *__restrict__ gd)
+// Plan + zero in one launch. Every block derives the same plan from bbox[parity] (filled by the
+// previous step's integration, or by k_bbox after an upload) and zeroes its share of
+// counts[0 .. ncells] (the extra entry becomes the end sentinel after the scan); block 0 publishes
+// the plan, re-arms bbox[parity^1] for this step's integration and resets the step counters.
+__global__ void __launch_bounds__(GRID_THREADS)
+k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, uint32_t *__restrict__ counts)
 {
-    const uint32_t n = gd->ncells + 1;
+    __shared__ GridDesc s_g;
+    if (threadIdx.x == 0) s_g = plan_grid(ctr->bbox[parity], max_cells);
+    __syncthreads();
+    const uint32_t n = s_g.ncells + 1;
     const uint32_t n4 = n >> 2;
     uint4 *c4 = reinterpret_cast<uint4 *>(counts);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
         c4[i] = make_uint4(0, 0, 0, 0);
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) counts[(n4 << 2) + threadIdx.x] = 0;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < (n & 3u)) counts[(n4 << 2) + threadIdx.x] = 0;
+        if (threadIdx.x == 0) {
+            *gd = s_g;
+            ctr->ticket = 0;
+            ctr->clamped = 0;
+            int *nb = ctr->bbox[parity ^ 1];
+            nb[0] = nb[1] = nb[2] = 0x7fffffff;
+            nb[3] = nb[4] = nb[5] = -0x7fffffff - 1;
+        }
+    }
 }
+
+// ---- histogram ------------------------------------------------------------------------------
 
 // One thread per particle (array is in last step's cell order, so neighbouring threads hit the
 // same or adjacent counters): cell -> grid index -> rank within the cell by atomicAdd.
@@ -300,21 +312,27 @@ k_stable_order(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_ra
     if (inverse) inverse[me.x] = s + k;
 }
 
-// Gather rows into cell order. pos.w (identity) rides along; vel.w becomes the hash16 of the
-// start-of-step cell.
+// Canonical order + gather in one pass: every slot finds its rank by particle id inside its cell
+// segment and moves its row straight to that place (a scatter confined to the cell segment).
+// pos.w (identity) rides along; the hash16 of the start-of-step cell goes to its own column.
 __global__ void __launch_bounds__(GRID_THREADS)
-k_gather_sorted(const uint32_t *__restrict__ order, uint32_t n_sorted, float h,
-                const float4 *__restrict__ pos_in, const float4 *__restrict__ vel_in,
-                float4 *__restrict__ pos_out, float4 *__restrict__ vel_out)
+k_order_gather(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_rank, uint32_t n_sorted,
+               const uint32_t *__restrict__ starts, float h, const float4 *__restrict__ pos_in,
+               const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
+               uint32_t *__restrict__ hash_out, uint32_t *__restrict__ inverse)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_sorted) return;
-    const uint32_t src = order[d];
-    const float4 p = pos_in[src];
-    float4 v = vel_in[src];
-    v.w = __uint_as_float(hash16_of(cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h)));
-    pos_out[d] = p;
-    vel_out[d] = v;
+    const uint2 me = slot[d];
+    const uint32_t c = cell_rank[me.x].x;
+    const uint32_t s = starts[c], e = starts[c + 1];
+    uint32_t k = s;
+    for (uint32_t t = s; t < e; ++t) k += (slot[t].y < me.y);
+    const float4 p = pos_in[me.x];
+    pos_out[k] = p;
+    vel_out[k] = vel_in[me.x];
+    hash_out[k] = hash16_of(cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h));
+    if (inverse) inverse[me.x] = k;
 }
 
 // Rows that survived the build (= the scan's end sentinel), published for the host.

@@ -9,7 +9,7 @@ namespace sphb {
 
 constexpr int IO_THREADS = 256;
 
-// xyz triples (+ optional ids) -> float4 rows. pos.w = id bits, vel.w = 0 (hash16 lane).
+// xyz triples (+ optional ids) -> float4 rows. pos.w = id bits, vel.w = 0 (density lane).
 __global__ void __launch_bounds__(IO_THREADS)
 k_import_xyz(const float *__restrict__ pos3, const float *__restrict__ vel3, const uint32_t *__restrict__ ids,
              uint32_t n, float4 *__restrict__ pos, float4 *__restrict__ vel)
@@ -54,7 +54,7 @@ struct ExportPtrs {
 
 __global__ void __launch_bounds__(IO_THREADS)
 k_export(const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float4 *__restrict__ force,
-         const float *__restrict__ rho, uint32_t n, const uint32_t *__restrict__ map, const Params P,
+         const uint32_t *__restrict__ hash16, uint32_t n, const uint32_t *__restrict__ map, const Params P,
          ExportPtrs out)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,9 +67,9 @@ k_export(const float4 *__restrict__ pos, const float4 *__restrict__ vel, const f
         const float4 f = force[r];
         out.force3[3 * d] = f.x; out.force3[3 * d + 1] = f.y; out.force3[3 * d + 2] = f.z;
     }
-    if (out.density) out.density[d] = rho[r];
-    if (out.pressure) out.pressure[d] = __fmul_rn(P.gas_constant, __fsub_rn(rho[r], P.rest_density));
-    if (out.hash16) out.hash16[d] = (uint16_t)(__float_as_uint(v.w) & W_HASH_MASK);
+    if (out.density) out.density[d] = v.w;
+    if (out.pressure) out.pressure[d] = __fmul_rn(P.gas_constant, __fsub_rn(v.w, P.rest_density));
+    if (out.hash16) out.hash16[d] = (uint16_t)(hash16[r] & W_HASH_MASK);
     if (out.id) out.id[d] = __float_as_uint(p.w);  // bit 31 set = ghost row (slab mode)
 }
 
@@ -118,14 +118,14 @@ k_import_aos(const uint32_t *__restrict__ aos, uint32_t n, float4 *__restrict__ 
 // (id = input row index).
 __global__ void __launch_bounds__(IO_THREADS)
 k_export_aos(const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float4 *__restrict__ force,
-             const float *__restrict__ rho, uint32_t n, const uint32_t *__restrict__ map, const Params P,
+             const uint32_t *__restrict__ hash16, uint32_t n, const uint32_t *__restrict__ map, const Params P,
              const uint32_t *__restrict__ aos_in, uint32_t *__restrict__ aos_out)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n) return;
     const uint32_t r = map ? map[d] : d;
     const float4 p = pos[r], v = vel[r], f = force[r];
-    const float rh = rho[r];
+    const float rh = v.w;
     const uint32_t id = __float_as_uint(p.w) & W_ID_MASK;
     const uint32_t *in = aos_in + (size_t)AOS_WORDS * id;
     uint32_t *o = aos_out + (size_t)AOS_WORDS * d;
@@ -135,18 +135,18 @@ k_export_aos(const float4 *__restrict__ pos, const float4 *__restrict__ vel, con
     o[9] = __float_as_uint(f.x); o[10] = __float_as_uint(f.y); o[11] = __float_as_uint(f.z);
     o[12] = __float_as_uint(rh);
     o[13] = __float_as_uint(__fmul_rn(P.gas_constant, __fsub_rn(rh, P.rest_density)));
-    o[14] = __float_as_uint(v.w) & W_HASH_MASK;
+    o[14] = hash16[r] & W_HASH_MASK;
 }
 
 // ---- hash16 ordering (order class of the reference's std::sort) and table ----------------------
 
 __global__ void __launch_bounds__(IO_THREADS)
-k_hash16_hist(const float4 *__restrict__ vel, uint32_t n, uint32_t *__restrict__ counts,
+k_hash16_hist(const uint32_t *__restrict__ hash16, uint32_t n, uint32_t *__restrict__ counts,
               uint2 *__restrict__ key_rank)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t k = __float_as_uint(vel[i].w) & W_HASH_MASK;
+    const uint32_t k = hash16[i] & W_HASH_MASK;
     const uint32_t r = atomicAdd(&counts[k], 1u);
     if (key_rank) key_rank[i] = make_uint2(k, r);
 }
@@ -173,8 +173,7 @@ struct StatsAccum {
 };
 
 __global__ void __launch_bounds__(IO_THREADS)
-k_stats(const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float *__restrict__ rho,
-        uint32_t n, StatsAccum *acc)
+k_stats(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, StatsAccum *acc)
 {
     double sr = 0.0, sv = 0.0;
     unsigned long long nn = 0;
@@ -182,7 +181,7 @@ k_stats(const float4 *__restrict__ pos, const float4 *__restrict__ vel, const fl
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pos[i], v = vel[i];
         if (__float_as_uint(p.w) & W_GHOST) continue;  // ghost or dropped row
-        const float r = rho[i];
+        const float r = v.w;
         if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) ++nn;
         sr += (double)r;
         sv += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z;

@@ -120,20 +120,20 @@ k_slab_pack_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
 
 // Densities of the rows a halo message was packed from (pre-sort row -> sorted row via inverse).
 __global__ void __launch_bounds__(SLAB_THREADS)
-k_slab_pack_density(const float *__restrict__ rho, const uint32_t *__restrict__ inverse,
+k_slab_pack_density(const float4 *__restrict__ vel, const uint32_t *__restrict__ inverse,
                     const uint32_t *__restrict__ rows, uint32_t nrows, float *__restrict__ out)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nrows) out[k] = rho[inverse[rows[k]]];
+    if (k < nrows) out[k] = vel[inverse[rows[k]]].w;  // density rides in vel.w
 }
 
 // Densities for a batch of ghost rows that was appended at pre-sort rows [first, first + nrows).
 __global__ void __launch_bounds__(SLAB_THREADS)
-k_slab_set_ghost_density(float *__restrict__ rho, const uint32_t *__restrict__ inverse, uint32_t first,
+k_slab_set_ghost_density(float4 *__restrict__ vel, const uint32_t *__restrict__ inverse, uint32_t first,
                          uint32_t nrows, const float *__restrict__ in)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < nrows) rho[inverse[first + k]] = in[k];
+    if (k < nrows) vel[inverse[first + k]].w = in[k];
 }
 
 // Histogram of cell.x over live owned rows, bins [x_lo, x_lo + nbins) with clamping at both ends
