@@ -258,6 +258,25 @@ int sph_slab_step_forces(sph_handle *h, float dt);
 /* Histogram of cell.x over owned rows, bins [x_cell_lo, x_cell_lo + nbins), ends clamped. */
 int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, uint64_t *host_hist);
 
+
+/* Sync-free variant of the same step for steady state: messages have a FIXED capacity and go
+ * only to the two adjacent ranks (NULL pointer = no neighbour on that side), unused message rows
+ * are dropped-row patterns (0xFF), and every count stays on the device, so the host enqueues a
+ * whole step without waiting for the GPU. The exact row count and any violation (message
+ * overflow, a particle that would have to travel further than the adjacent slab) are read back
+ * one step late by the next sph_slab_fast_begin, which then fails with SPH_ERR_CAPACITY: use the
+ * general path above for the step after cuts change.
+ * Order: fast_begin -> exchange migrants -> fast_arrivals -> fast_halo -> exchange -> fast_ghosts
+ * -> sph_slab_step_density -> fast_pack_density -> exchange -> fast_set_ghost_density ->
+ * sph_slab_step_forces. Row messages hold cap_rows x 32 bytes, density messages cap_rows floats. */
+int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next, uint64_t cap_rows,
+                        void *dev_send_left, void *dev_send_right);
+int sph_slab_fast_arrivals(sph_handle *h, const void *dev_recv_left, const void *dev_recv_right, uint64_t cap_rows);
+int sph_slab_fast_halo(sph_handle *h, int32_t lo, int32_t hi, uint64_t cap_rows, void *dev_send_left, void *dev_send_right);
+int sph_slab_fast_ghosts(sph_handle *h, const void *dev_recv_left, const void *dev_recv_right, uint64_t cap_rows);
+int sph_slab_fast_pack_density(sph_handle *h, uint64_t cap_rows, void *dev_send_left, void *dev_send_right);
+int sph_slab_fast_set_ghost_density(sph_handle *h, const void *dev_recv_left, const void *dev_recv_right, uint64_t cap_rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,12 @@ def load_library() -> C.CDLL:
         "sph_slab_step_forces": ([hp, C.c_float], C.c_int),
         "sph_slab_xcell_histogram": ([hp, C.c_int32, C.c_uint32, u64p], C.c_int),
         "sph_scene_block_slice": ([C.c_int] * 3 + [C.c_float] * 5 + [C.c_uint, C.c_int, C.c_int, fp, fp, u32p], C.c_int),
+        "sph_slab_fast_begin": ([hp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p], C.c_int),
+        "sph_slab_fast_arrivals": ([hp, C.c_void_p, C.c_void_p, C.c_uint64], C.c_int),
+        "sph_slab_fast_halo": ([hp, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p], C.c_int),
+        "sph_slab_fast_ghosts": ([hp, C.c_void_p, C.c_void_p, C.c_uint64], C.c_int),
+        "sph_slab_fast_pack_density": ([hp, C.c_uint64, C.c_void_p, C.c_void_p], C.c_int),
+        "sph_slab_fast_set_ghost_density": ([hp, C.c_void_p, C.c_void_p, C.c_uint64], C.c_int),
         "sph_system_create": ([C.c_int, sp, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
         "sph_system_destroy": ([hp], C.c_int),
         "sph_system_last_error": ([hp], C.c_char_p),

@@ -55,7 +55,12 @@ struct sph_handle {
     uint64_t ghost_first[2] = {0, 0}, ghost_n[2] = {0, 0};  // appended ghost batches (pre-sort rows)
     uint64_t n_ghost = 0;                 // ghost rows among the n rows
     bool slab_mode = false;
-    int forces_cfg = 0;
+    bool slab_fast = false;       // sync-free slab path: exact row count is read back one step late
+    bool rows_pending = false;    // pinned_rows holds a newer row count than h->n
+    uint32_t *pinned_rows = nullptr;  // [0] rows surviving the last build, [1] slab violation bits
+    cudaEvent_t ev_rows = nullptr;
+    uint64_t fast_halo_cap = 0;
+    int forces_cfg = 0, density_cfg = 0;
     unsigned long long *slab_counts = nullptr;  // SLAB_MAX_RANKS counters + cursors
     uint32_t *cells = nullptr;
     uint32_t max_cells = 0;
@@ -172,6 +177,32 @@ int enter(sph_handle *h)
     return SPH_OK;
 }
 
+// Sync-free slab path: pick up the exact row count (and violation bits) the last build published.
+int resolve_rows(sph_handle *h)
+{
+    if (!h->rows_pending) return SPH_OK;
+    CK(cudaEventSynchronize(h->ev_rows));
+    h->rows_pending = false;
+    h->n = h->pinned_rows[0];
+    const uint32_t err = h->pinned_rows[1];
+    if (err)
+        return fail(h, SPH_ERR_CAPACITY,
+                    "slab exchange violation in the previous step:%s%s%s (raise the message capacities or rebalance with the "
+                    "general path)",
+                    (err & SLAB_ERR_MIGRANT_OVERFLOW) ? " migrant message overflow" : "",
+                    (err & SLAB_ERR_HALO_OVERFLOW) ? " halo message overflow" : "",
+                    (err & SLAB_ERR_NOT_ADJACENT) ? " a particle left for a non-adjacent slab" : "");
+    return SPH_OK;
+}
+
+// For calls that need the exact row count on the host (downloads, diagnostics, the general slab path).
+int enter_exact(sph_handle *h)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    return resolve_rows(h);
+}
+
 // bbox of the current positions into bbox[parity] (after an upload; in steady state the
 // integration kernel has already produced it).
 int compute_bbox(sph_handle *h)
@@ -206,20 +237,48 @@ int build_grid(sph_handle *h)
     k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot);
     CK_LAUNCH();
     uint32_t n_sorted = n;
+    const uint32_t *n_dev = nullptr;
     if (h->slab_mode) {
         k_publish_rows<<<1, 32, 0, s>>>(h->cells, h->gd, h->ctr);
         CK_LAUNCH();
-        CK(cudaMemcpyAsync(&n_sorted, &h->ctr->aux[2], sizeof n_sorted, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        if (h->slab_fast) {
+            // No host sync: later kernels run over the bound n and skip the dropped tail; the exact
+            // count (and the violation bits next to it) reach the host before the next step.
+            CK(cudaMemcpyAsync(h->pinned_rows, &h->ctr->aux[2], 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(h->ev_rows, s));
+            h->rows_pending = true;
+            n_dev = &h->ctr->aux[2];
+        } else {
+            CK(cudaMemcpyAsync(&n_sorted, &h->ctr->aux[2], sizeof n_sorted, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
     }
     if (n_sorted) {
         k_order_gather<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
-            h->slot, h->cell_rank, n_sorted, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1],
+            h->slot, h->cell_rank, n_sorted, n_dev, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1],
             h->vel[h->cur ^ 1], h->hash16, h->slab_mode ? h->inverse : nullptr);
         CK_LAUNCH();
     }
     h->cur ^= 1;
     h->n = n_sorted;
+    return SPH_OK;
+}
+
+// Launch-shape variants of the density kernel (SPH_B200_DENSITY_CFG, experiments).
+int launch_density(sph_handle *h, uint32_t n)
+{
+#define LAUNCH_D(S, B)                                                                                     \
+    k_density<S, B><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(                             \
+        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap)
+    switch (h->density_cfg) {
+    case 1: LAUNCH_D(16, 16); break;
+    case 2: LAUNCH_D(24, 12); break;
+    case 3: LAUNCH_D(16, 12); break;
+    case 4: LAUNCH_D(12, 16); break;
+    default: LAUNCH_D(24, 1); break;
+    }
+#undef LAUNCH_D
+    CK_LAUNCH();
     return SPH_OK;
 }
 
@@ -263,9 +322,8 @@ int step_once(sph_handle *h, float dt)
     int rc = build_grid(h);
     if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[1], s));
-    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P,
-                                                                 h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap);
-    CK_LAUNCH();
+    rc = launch_density(h, n);
+    if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[2], s));
     rc = launch_forces_integrate(h, n, dt);
     if (rc) return rc;
@@ -405,6 +463,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     nh->max_cells = (uint32_t)mc;
     nh->forces_cfg = 2;  // 128 threads, <= 48 registers: the pass is latency-bound, occupancy wins
     if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
+    if (const char *e = std::getenv("SPH_B200_DENSITY_CFG")) nh->density_cfg = std::atoi(e);
 
     const size_t cap = (size_t)capacity;
     for (int b = 0; b < 2; ++b) {
@@ -434,6 +493,9 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaMemsetAsync(nh->ctr, 0, sizeof(StepCounters), nh->stream));
     CKC(cudaMemsetAsync(nh->gd, 0, sizeof(GridDesc), nh->stream));
     CKC(cudaMalloc(&nh->stats_acc, sizeof(StatsAccum)));
+    CKC(cudaHostAlloc(&nh->pinned_rows, 2 * sizeof(uint32_t), cudaHostAllocDefault));
+    nh->pinned_rows[0] = nh->pinned_rows[1] = 0;
+    CKC(cudaEventCreateWithFlags(&nh->ev_rows, cudaEventDisableTiming));
     const uint32_t c65536 = 65536u;
     CKC(cudaMemcpyAsync(nh->const_65536, &c65536, sizeof c65536, cudaMemcpyHostToDevice, nh->stream));
     CKC(cudaStreamSynchronize(nh->stream));
@@ -453,6 +515,8 @@ int sph_destroy(sph_handle *h)
     cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
     cudaFree(h->stats_acc); cudaFree(h->scratch);
+    if (h->pinned_rows) cudaFreeHost(h->pinned_rows);
+    if (h->ev_rows) cudaEventDestroy(h->ev_rows);
     for (auto &pe : h->ev_pool)
         for (auto &e : pe.e) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -462,7 +526,7 @@ int sph_destroy(sph_handle *h)
 
 int sph_set_settings(sph_handle *h, const sph_settings *s)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     rc = validate_settings(h, s);
     if (rc) return rc;
@@ -483,7 +547,7 @@ void *sph_stream(sph_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 int sph_upload(sph_handle *h, uint64_t n, const float *host_pos, const float *host_vel, const uint32_t *host_id)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "upload of %llu particles exceeds capacity %llu",
                                 (unsigned long long)n, (unsigned long long)h->cap);
@@ -510,7 +574,7 @@ int sph_upload(sph_handle *h, uint64_t n, const float *host_pos, const float *ho
 
 int sph_upload_device(sph_handle *h, uint64_t n, const void *dev_pos, const void *dev_vel)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "upload of %llu particles exceeds capacity %llu",
                                 (unsigned long long)n, (unsigned long long)h->cap);
@@ -529,7 +593,7 @@ int sph_upload_device(sph_handle *h, uint64_t n, const void *dev_pos, const void
 int sph_download(sph_handle *h, int order, float *host_pos, float *host_vel, float *host_force, float *host_density,
                  float *host_pressure, uint16_t *host_hash16, uint32_t *host_id)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
     if ((host_force || host_density || host_pressure || host_hash16 || order == SPH_ORDER_HASH16) && !h->have_step)
@@ -583,7 +647,7 @@ int sph_download(sph_handle *h, int order, float *host_pos, float *host_vel, flo
 
 int sph_read_positions_device(sph_handle *h, void *dev_xyzw)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
     if (!dev_xyzw) return fail(h, SPH_ERR_INVALID, "destination is NULL");
@@ -597,7 +661,7 @@ int sph_read_positions_device(sph_handle *h, void *dev_xyzw)
 
 int sph_read_positions(sph_handle *h, float *host_xyzw)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!host_xyzw) return fail(h, SPH_ERR_INVALID, "destination is NULL");
     rc = ensure_scratch(h, sizeof(float4) * h->n + 256);
@@ -611,7 +675,7 @@ int sph_read_positions(sph_handle *h, float *host_xyzw)
 
 int sph_write_transforms_device(sph_handle *h, void *dev_mat4)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
     if (!dev_mat4) return fail(h, SPH_ERR_INVALID, "destination is NULL");
@@ -625,7 +689,7 @@ int sph_write_transforms_device(sph_handle *h, void *dev_mat4)
 
 int sph_write_transforms(sph_handle *h, float *host_mat4)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!host_mat4) return fail(h, SPH_ERR_INVALID, "destination is NULL");
     rc = ensure_scratch(h, 64 * h->n + 256);
@@ -641,7 +705,7 @@ int sph_write_transforms(sph_handle *h, float *host_mat4)
 
 int sph_step(sph_handle *h, float dt, int nsteps)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "sph_step before sph_upload");
     if (nsteps < 0) return fail(h, SPH_ERR_INVALID, "nsteps must be >= 0");
@@ -656,7 +720,7 @@ int sph_step(sph_handle *h, float dt, int nsteps)
 
 int sph_sync(sph_handle *h)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return SPH_OK;
@@ -664,7 +728,7 @@ int sph_sync(sph_handle *h)
 
 int sph_update_particles_aos(sph_handle *h, void *host_particles, float *host_mat4, uint64_t n, float dt)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "%llu particles exceed capacity %llu", (unsigned long long)n,
                                 (unsigned long long)h->cap);
@@ -705,7 +769,7 @@ int sph_update_particles_aos(sph_handle *h, void *host_particles, float *host_ma
 
 int sph_hash_table(sph_handle *h, uint32_t *host_table)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_step) return fail(h, SPH_ERR_STATE, "the hash table is only defined after a step");
     if (!host_table) return fail(h, SPH_ERR_INVALID, "destination is NULL");
@@ -723,7 +787,7 @@ int sph_hash_table(sph_handle *h, uint32_t *host_table)
 int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offsets, uint32_t *host_list,
                        uint64_t list_capacity, uint32_t *host_ids_out)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
     if (!host_counts) return fail(h, SPH_ERR_INVALID, "counts is NULL");
@@ -736,9 +800,8 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
     rc = build_grid(h);
     if (rc) return rc;
     // The density pass writes the lists the force pass consumes; report exactly those.
-    k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], (uint32_t)n, h->gd, h->cells, h->P,
-                                                                         h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap);
-    CK_LAUNCH();
+    rc = launch_density(h, (uint32_t)n);
+    if (rc) return rc;
     uint32_t *dcounts = reinterpret_cast<uint32_t *>(h->slot);  // free after build_grid
     k_neighbor_lists<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], h->vel[h->cur], (uint32_t)n,
                                                                                 h->gd, h->cells, h->P, h->nlist, h->ncount,
@@ -782,7 +845,7 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
 
 int sph_get_stats(sph_handle *h, sph_stats *out)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!out) return fail(h, SPH_ERR_INVALID, "out is NULL");
     std::memset(out, 0, sizeof *out);
@@ -806,7 +869,8 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     out->grid_cells = g.ncells;
     out->clamped = c.clamped;
     out->nan_count = a.nan_count;
-    out->mean_density = a.sum_rho / (double)(h->n - h->n_ghost ? h->n - h->n_ghost : 1);
+    if (h->have_step) out->count = a.owned;
+    out->mean_density = a.sum_rho / (double)(a.owned ? a.owned : 1);
     float mx;
     std::memcpy(&mx, &a.max_rho_bits, 4);
     out->max_density = mx;
@@ -904,7 +968,7 @@ uint64_t sph_slab_owned(const sph_handle *h) { return h ? h->n - h->n_ghost : 0;
 
 int sph_slab_count(sph_handle *h, const int32_t *cuts, int world, uint64_t *host_counts)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
     if (!host_counts) return fail(h, SPH_ERR_INVALID, "counts is NULL");
@@ -926,7 +990,7 @@ int sph_slab_count(sph_handle *h, const int32_t *cuts, int world, uint64_t *host
 
 int sph_slab_pack(sph_handle *h, const int32_t *cuts, int world, int self, void *dev_buf, const uint64_t *row_offsets)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
     if (self < 0 || self >= world || !row_offsets) return fail(h, SPH_ERR_INVALID, "bad self / offsets");
@@ -945,6 +1009,7 @@ int sph_slab_pack(sph_handle *h, const int32_t *cuts, int world, int self, void 
     h->n_ghost = 0;  // last step's ghosts are dropped rows now
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
+    h->slab_fast = false;
     return SPH_OK;
 }
 
@@ -975,7 +1040,7 @@ int sph_slab_append(sph_handle *h, const void *dev_rows, uint64_t nrows, int kin
 
 int sph_slab_pack_halo(sph_handle *h, int32_t cell_x, int side, void *dev_buf, uint64_t capacity_rows, uint64_t *nrows_out)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (side < 0 || side > 1 || !nrows_out) return fail(h, SPH_ERR_INVALID, "bad side / nrows_out");
     unsigned long long *cursor = h->slab_counts + 2 * SLAB_MAX_RANKS + side;
@@ -1009,9 +1074,8 @@ int sph_slab_step_density(sph_handle *h)
     if (rc) return rc;
     const uint32_t n = (uint32_t)h->n;
     if (n) {
-        k_density<<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur], n, h->gd, h->cells, h->P,
-                                                                             h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap);
-        CK_LAUNCH();
+        rc = launch_density(h, n);
+        if (rc) return rc;
     }
     h->launches += 6;
     return SPH_OK;
@@ -1068,7 +1132,7 @@ int sph_slab_step_forces(sph_handle *h, float dt)
 
 int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, uint64_t *host_hist)
 {
-    int rc = enter(h);
+    int rc = enter_exact(h);
     if (rc) return rc;
     if (!host_hist || nbins == 0 || nbins > (1u << 24)) return fail(h, SPH_ERR_INVALID, "bad histogram arguments");
     rc = ensure_scratch(h, sizeof(unsigned long long) * nbins + 256);
@@ -1082,6 +1146,124 @@ int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, u
     }
     CK(cudaMemcpyAsync(host_hist, d, sizeof(unsigned long long) * nbins, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return SPH_OK;
+}
+
+// ---- sync-free slab path: fixed-size messages to the adjacent ranks, no host synchronisation ----
+
+int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next, uint64_t cap_rows,
+                        void *dev_send_left, void *dev_send_right)
+{
+    int rc = enter_exact(h);  // the only wait of the step: the row count of the PREVIOUS step's build
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!h->slab_mode) return fail(h, SPH_ERR_STATE, "call sph_slab_enable(h, 1) first");
+    if (cap_rows == 0 || cap_rows > h->cap) return fail(h, SPH_ERR_INVALID, "bad message capacity");
+    cudaStream_t s = h->stream;
+    unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;  // [0,1] migrants, [2,3] halos
+    CK(cudaMemsetAsync(cur, 0, 4 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(&h->ctr->aux[3], 0, sizeof(uint32_t), s));
+    if (dev_send_left) CK(cudaMemsetAsync(dev_send_left, 0xFF, cap_rows * 32, s));
+    if (dev_send_right) CK(cudaMemsetAsync(dev_send_right, 0xFF, cap_rows * 32, s));
+    if (h->n) {
+        k_slab_fast_begin<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dev_send_left ? lo : -0x7fffffff - 1,
+            dev_send_right ? hi : 0x7fffffff, lo_prev, hi_next, (uint32_t)cap_rows, (float4 *)dev_send_left,
+            (float4 *)dev_send_right, cur, &h->ctr->aux[3]);
+        CK_LAUNCH();
+    }
+    h->slab_fast = true;
+    h->n_ghost = 0;
+    h->ghost_n[0] = h->ghost_n[1] = 0;
+    h->have_step = false;
+    ++h->launches;
+    return SPH_OK;
+}
+
+// Append two fixed-size row messages (either may be NULL) after the current rows.
+static int fast_append(sph_handle *h, const void *left, const void *right, uint64_t cap_rows, bool ghost)
+{
+    const void *src[2] = {left, right};
+    for (int side = 0; side < 2; ++side) {
+        if (ghost) { h->ghost_first[side] = h->n; h->ghost_n[side] = src[side] ? cap_rows : 0; }
+        if (!src[side]) continue;
+        if (h->n + cap_rows > h->cap)
+            return fail(h, SPH_ERR_CAPACITY, "appending a %llu-row message to %llu rows exceeds capacity %llu",
+                        (unsigned long long)cap_rows, (unsigned long long)h->n, (unsigned long long)h->cap);
+        k_slab_append<<<blocks_for(cap_rows, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            (const float4 *)src[side], (uint32_t)cap_rows, (uint32_t)h->n, ghost, h->pos[h->cur], h->vel[h->cur]);
+        CK_LAUNCH();
+        h->n += cap_rows;
+        ++h->launches;
+    }
+    return SPH_OK;
+}
+
+int sph_slab_fast_arrivals(sph_handle *h, const void *dev_recv_left, const void *dev_recv_right, uint64_t cap_rows)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    return fast_append(h, dev_recv_left, dev_recv_right, cap_rows, false);
+}
+
+int sph_slab_fast_halo(sph_handle *h, int32_t lo, int32_t hi, uint64_t cap_rows, void *dev_send_left, void *dev_send_right)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (cap_rows == 0 || cap_rows > h->cap) return fail(h, SPH_ERR_INVALID, "bad message capacity");
+    cudaStream_t s = h->stream;
+    if (dev_send_left) CK(cudaMemsetAsync(dev_send_left, 0xFF, cap_rows * 32, s));
+    if (dev_send_right) CK(cudaMemsetAsync(dev_send_right, 0xFF, cap_rows * 32, s));
+    if (h->n) {
+        k_slab_fast_halo<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dev_send_left != nullptr,
+            dev_send_right != nullptr, (uint32_t)cap_rows, (float4 *)dev_send_left, (float4 *)dev_send_right,
+            h->halo_rows[0], h->halo_rows[1], h->slab_counts + 2 * SLAB_MAX_RANKS, &h->ctr->aux[3]);
+        CK_LAUNCH();
+    }
+    h->fast_halo_cap = cap_rows;
+    ++h->launches;
+    return SPH_OK;
+}
+
+int sph_slab_fast_ghosts(sph_handle *h, const void *dev_recv_left, const void *dev_recv_right, uint64_t cap_rows)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    return fast_append(h, dev_recv_left, dev_recv_right, cap_rows, true);
+}
+
+int sph_slab_fast_pack_density(sph_handle *h, uint64_t cap_rows, void *dev_send_left, void *dev_send_right)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (cap_rows != h->fast_halo_cap) return fail(h, SPH_ERR_INVALID, "capacity differs from the halo messages'");
+    void *dst[2] = {dev_send_left, dev_send_right};
+    for (int side = 0; side < 2; ++side) {
+        if (!dst[side]) continue;
+        CK(cudaMemsetAsync(dst[side], 0xFF, cap_rows * sizeof(float), h->stream));
+        k_slab_fast_pack_density<<<blocks_for(cap_rows, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            h->vel[h->cur], h->inverse, h->halo_rows[side], h->slab_counts + 2 * SLAB_MAX_RANKS + 2 + side,
+            (uint32_t)cap_rows, (float *)dst[side]);
+        CK_LAUNCH();
+        ++h->launches;
+    }
+    return SPH_OK;
+}
+
+int sph_slab_fast_set_ghost_density(sph_handle *h, const void *dev_recv_left, const void *dev_recv_right, uint64_t cap_rows)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    const void *src[2] = {dev_recv_left, dev_recv_right};
+    for (int side = 0; side < 2; ++side) {
+        if (!src[side] || h->ghost_n[side] == 0) continue;
+        if (cap_rows != h->ghost_n[side]) return fail(h, SPH_ERR_INVALID, "capacity differs from the ghost batch's");
+        k_slab_fast_set_ghost_density<<<blocks_for(cap_rows, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            h->vel[h->cur], h->inverse, (uint32_t)h->ghost_first[side], (uint32_t)cap_rows, (const float *)src[side]);
+        CK_LAUNCH();
+        ++h->launches;
+    }
     return SPH_OK;
 }
 

@@ -316,13 +316,19 @@ k_stable_order(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_ra
 // segment and moves its row straight to that place (a scatter confined to the cell segment).
 // pos.w (identity) rides along; the hash16 of the start-of-step cell goes to its own column.
 __global__ void __launch_bounds__(GRID_THREADS)
-k_order_gather(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_rank, uint32_t n_sorted,
-               const uint32_t *__restrict__ starts, float h, const float4 *__restrict__ pos_in,
-               const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out, float4 *__restrict__ vel_out,
-               uint32_t *__restrict__ hash_out, uint32_t *__restrict__ inverse)
+k_order_gather(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_rank, uint32_t n_bound,
+               const uint32_t *__restrict__ n_sorted_dev, const uint32_t *__restrict__ starts, float h,
+               const float4 *__restrict__ pos_in, const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out,
+               float4 *__restrict__ vel_out, uint32_t *__restrict__ hash_out, uint32_t *__restrict__ inverse)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_sorted) return;
+    if (d >= n_bound) return;
+    // Sync-free slab mode: the host only knows an upper bound of the surviving rows; the exact
+    // count is on the device. Rows past it become dropped rows, which every later kernel skips.
+    if (n_sorted_dev && d >= *n_sorted_dev) {
+        pos_out[d] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
+        return;
+    }
     const uint2 me = slot[d];
     const uint32_t c = cell_rank[me.x].x;
     const uint32_t s = starts[c], e = starts[c + 1];

@@ -167,7 +167,7 @@ k_ref_table(const uint32_t *__restrict__ starts65537, uint32_t *__restrict__ tab
 
 struct StatsAccum {
     double sum_rho, sum_v2;
-    unsigned long long nan_count;
+    unsigned long long nan_count, owned;
     uint32_t max_rho_bits;  // densities are positive: uint order == float order
     uint32_t pad_;
 };
@@ -176,11 +176,12 @@ __global__ void __launch_bounds__(IO_THREADS)
 k_stats(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, StatsAccum *acc)
 {
     double sr = 0.0, sv = 0.0;
-    unsigned long long nn = 0;
+    unsigned long long nn = 0, no = 0;
     float mx = 0.f;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 p = pos[i], v = vel[i];
         if (__float_as_uint(p.w) & W_GHOST) continue;  // ghost or dropped row
+        ++no;
         const float r = v.w;
         if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) ++nn;
         sr += (double)r;
@@ -191,12 +192,14 @@ k_stats(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t
         sr += __shfl_xor_sync(0xffffffffu, sr, o);
         sv += __shfl_xor_sync(0xffffffffu, sv, o);
         nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        no += __shfl_xor_sync(0xffffffffu, no, o);
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&acc->sum_rho, sr);
         atomicAdd(&acc->sum_v2, sv);
         atomicAdd(&acc->nan_count, nn);
+        atomicAdd(&acc->owned, no);
         atomicMax(&acc->max_rho_bits, __float_as_uint(mx));
     }
 }

@@ -81,7 +81,9 @@ k_slab_pack(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n
     }
 }
 
-// Append received rows after the current rows, as owned particles or as ghosts.
+// Append received rows after the current rows, as owned particles or as ghosts. Rows whose id
+// lane is the dropped-row pattern (the unused tail of a fixed-size message, pre-filled with 0xFF)
+// stay dropped rows.
 __global__ void __launch_bounds__(SLAB_THREADS)
 k_slab_append(const float4 *__restrict__ rows, uint32_t nrows, uint32_t first, bool ghost,
               float4 *__restrict__ pos, float4 *__restrict__ vel)
@@ -90,11 +92,114 @@ k_slab_append(const float4 *__restrict__ rows, uint32_t nrows, uint32_t first, b
     if (k >= nrows) return;
     float4 p = rows[2 * k];
     const float4 v = rows[2 * k + 1];
-    uint32_t w = __float_as_uint(p.w) & W_ID_MASK;
-    if (ghost) w |= W_GHOST;
+    uint32_t w = __float_as_uint(p.w);
+    if (w != W_DROP) {
+        w &= W_ID_MASK;
+        if (ghost) w |= W_GHOST;
+    }
     p.w = __uint_as_float(w);
     pos[first + k] = p;
     vel[first + k] = v;
+}
+
+// ---- sync-free path: fixed-size messages to the two adjacent ranks, counts stay on the device ----
+
+// Violation bits accumulated in StepCounters::aux[3] and read back one step late.
+constexpr uint32_t SLAB_ERR_MIGRANT_OVERFLOW = 1u, SLAB_ERR_HALO_OVERFLOW = 2u, SLAB_ERR_NOT_ADJACENT = 4u;
+
+// One pass over the rows: last step's ghosts are dropped; owned rows whose cell.x left [lo, hi)
+// are copied to the left / right migrant message (pre-filled with dropped rows by the caller)
+// and dropped here. cur[0], cur[1] = message cursors (start at 0). A row that would have to travel
+// further than the adjacent rank, or does not fit, raises a violation bit and stays put.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int lo, int hi,
+                  int lo_prev, int hi_next, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
+                  unsigned long long *__restrict__ cur, uint32_t *__restrict__ err)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    const uint32_t w = __float_as_uint(p.w);
+    if (w == W_DROP) return;
+    bool drop = (w & W_GHOST) != 0u;
+    if (!drop) {
+        const int cx = cell_of(p.x, h);
+        const int side = cx < lo ? 0 : (cx >= hi ? 1 : -1);
+        if (side >= 0) {
+            if ((side == 0 && cx < lo_prev) || (side == 1 && cx >= hi_next)) {
+                atomicOr(err, SLAB_ERR_NOT_ADJACENT);
+            } else {
+                const unsigned long long k = atomicAdd(&cur[side], 1ull);
+                if (k >= cap) {
+                    atomicOr(err, SLAB_ERR_MIGRANT_OVERFLOW);
+                } else {
+                    float4 *dst = side == 0 ? send_l : send_r;
+                    float4 v = vel[i];
+                    v.w = 0.f;
+                    dst[2 * k] = p;
+                    dst[2 * k + 1] = v;
+                    drop = true;
+                }
+            }
+        }
+    }
+    if (drop) {
+        p.w = __uint_as_float(W_DROP);
+        pos[i] = p;
+    }
+}
+
+// Both halo messages in one pass: owned rows of x-cell lo go left, of x-cell hi-1 go right (a
+// one-cell slab sends its rows both ways). cur[2], cur[3] = cursors; rows_l / rows_r remember the
+// source rows so the densities can follow in the same order.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_fast_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int lo, int hi,
+                 bool has_left, bool has_right, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
+                 uint32_t *__restrict__ rows_l, uint32_t *__restrict__ rows_r, unsigned long long *__restrict__ cur,
+                 uint32_t *__restrict__ err)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    const uint32_t w = __float_as_uint(p.w);
+    if (w == W_DROP || (w & W_GHOST)) return;
+    const int cx = cell_of(p.x, h);
+    const bool to_l = has_left && cx == lo, to_r = has_right && cx == hi - 1;
+    if (!to_l && !to_r) return;
+    float4 v = vel[i];
+    v.w = 0.f;
+    if (to_l) {
+        const unsigned long long k = atomicAdd(&cur[2], 1ull);
+        if (k < cap) { send_l[2 * k] = p; send_l[2 * k + 1] = v; rows_l[k] = i; }
+        else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
+    }
+    if (to_r) {
+        const unsigned long long k = atomicAdd(&cur[3], 1ull);
+        if (k < cap) { send_r[2 * k] = p; send_r[2 * k + 1] = v; rows_r[k] = i; }
+        else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
+    }
+}
+
+// Densities of the rows of one halo message; the message count is on the device (cursor). The
+// output was pre-filled with 0xFF words, which the receiver treats as "no row".
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_fast_pack_density(const float4 *__restrict__ vel, const uint32_t *__restrict__ inverse,
+                         const uint32_t *__restrict__ rows, const unsigned long long *__restrict__ count, uint32_t cap,
+                         float *__restrict__ out)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long c = *count;
+    if (k < cap && k < c) out[k] = vel[inverse[rows[k]]].w;
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_fast_set_ghost_density(float4 *__restrict__ vel, const uint32_t *__restrict__ inverse, uint32_t first,
+                              uint32_t cap, const float *__restrict__ in)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cap) return;
+    const float r = in[k];
+    if (__float_as_uint(r) != 0xFFFFFFFFu) vel[inverse[first + k]].w = r;
 }
 
 // Copy the live owned rows of x-cell `cell_x` (a boundary layer of the slab) into a halo

@@ -116,6 +116,30 @@ class GpuEngine:
     def sync(self):
         self.sim.sync()
 
+    # -- sync-free path: fixed-size messages, tensors may be None (no neighbour on that side) --------
+    @staticmethod
+    def _p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    def fast_begin(self, lo, hi, lo_prev, hi_next, cap, send_l, send_r):
+        self._ck(self.lib.sph_slab_fast_begin(self.sim.handle, int(lo), int(hi), int(lo_prev), int(hi_next), cap,
+                                              self._p(send_l), self._p(send_r)))
+
+    def fast_arrivals(self, recv_l, recv_r, cap):
+        self._ck(self.lib.sph_slab_fast_arrivals(self.sim.handle, self._p(recv_l), self._p(recv_r), cap))
+
+    def fast_halo(self, lo, hi, cap, send_l, send_r):
+        self._ck(self.lib.sph_slab_fast_halo(self.sim.handle, int(lo), int(hi), cap, self._p(send_l), self._p(send_r)))
+
+    def fast_ghosts(self, recv_l, recv_r, cap):
+        self._ck(self.lib.sph_slab_fast_ghosts(self.sim.handle, self._p(recv_l), self._p(recv_r), cap))
+
+    def fast_pack_density(self, cap, send_l, send_r):
+        self._ck(self.lib.sph_slab_fast_pack_density(self.sim.handle, cap, self._p(send_l), self._p(send_r)))
+
+    def fast_set_ghost_density(self, recv_l, recv_r, cap):
+        self._ck(self.lib.sph_slab_fast_set_ghost_density(self.sim.handle, self._p(recv_l), self._p(recv_r), cap))
+
 
 # ------------------------------------------------------------------------------------------------
 # cuts
@@ -282,6 +306,80 @@ class SlabDriver:
         self.stats["steps"] += 1
 
 
+    # -- sync-free step --------------------------------------------------------------------------
+    def setup_fast(self, halo_rows: int, migrant_rows: int | None = None):
+        """Allocate the fixed-size message buffers of the sync-free path. halo_rows must exceed the
+        population of a boundary x-cell layer, migrant_rows the particles crossing a cut per step."""
+        e, r, w = self.e, self.rank, self.world
+        self.fast_H = int(halo_rows)
+        self.fast_M = int(migrant_rows if migrant_rows is not None else max(4096, halo_rows // 8))
+        has = (r > 0, r < w - 1)
+        with self._in_stream():
+            mk = lambda n: [e.empty_rows(n) if has[k] else None for k in range(2)]
+            mkf = lambda n: [e.empty_floats(n) if has[k] else None for k in range(2)]
+            self.f_mig_s, self.f_mig_r = mk(self.fast_M), mk(self.fast_M)
+            self.f_halo_s, self.f_halo_r = mk(self.fast_H), mk(self.fast_H)
+            self.f_rho_s, self.f_rho_r = mkf(self.fast_H), mkf(self.fast_H)
+
+    def suggest_halo_rows(self, slack: float = 3.0) -> int:
+        """A message capacity from the global cell.x histogram: `slack` times the fullest layer
+        adjacent to any cut (call after rebalance(); collective)."""
+        with self._in_stream():
+            hist = torch.from_numpy(self.e.xcell_histogram(self.x_lo, self.nbins))
+            if self.backend == "nccl":
+                hist = hist.to(self.e.device)
+            if self.world > 1:
+                dist.all_reduce(hist, group=self.group)
+            hist = hist.cpu().numpy()
+        worst = 1
+        for c in self.cuts[1:-1]:
+            b = c - self.x_lo
+            worst = max(worst, int(hist[max(b - 2, 0):b + 2].max()))
+        return int(max(4096, slack * worst))
+
+    def _p2p(self, send, recv):
+        """Exchange fixed-size messages with the adjacent ranks (send/recv = [left, right])."""
+        r, w = self.rank, self.world
+        ops, staged = [], []
+        for side, peer in ((0, r - 1), (1, r + 1)):
+            if peer < 0 or peer >= w:
+                continue
+            s_t, r_t = send[side], recv[side]
+            if self.backend == "gloo" and s_t.is_cuda:  # tests: two ranks on one GPU, host staging
+                s_c, r_c = s_t.cpu(), torch.empty(r_t.shape, dtype=r_t.dtype)
+                staged.append((r_t, r_c))
+                s_t, r_t = s_c, r_c
+            ops.append(dist.P2POp(dist.isend, s_t, peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, r_t, peer, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()  # NCCL: orders the library's stream after the transfer, no host wait
+        for dst, src in staged:
+            dst.copy_(src)
+
+    def step_fast(self, dt: float = 0.0):
+        """One step with no host synchronisation except picking up last step's row count. Valid
+        while the cuts are unchanged since the last general step()."""
+        e, r, w = self.e, self.rank, self.world
+        c = self.cuts
+        lo, hi = c[r], c[r + 1]
+        lo_prev = c[r - 1] if r > 0 else INT_MIN
+        hi_next = c[r + 2] if r < w - 1 else INT_MAX
+        with self._in_stream():
+            e.fast_begin(lo, hi, lo_prev, hi_next, self.fast_M, self.f_mig_s[0], self.f_mig_s[1])
+            self._p2p(self.f_mig_s, self.f_mig_r)
+            e.fast_arrivals(self.f_mig_r[0], self.f_mig_r[1], self.fast_M)
+            e.fast_halo(lo, hi, self.fast_H, self.f_halo_s[0], self.f_halo_s[1])
+            self._p2p(self.f_halo_s, self.f_halo_r)
+            e.fast_ghosts(self.f_halo_r[0], self.f_halo_r[1], self.fast_H)
+            e.step_density()
+            e.fast_pack_density(self.fast_H, self.f_rho_s[0], self.f_rho_s[1])
+            self._p2p(self.f_rho_s, self.f_rho_r)
+            e.fast_set_ghost_density(self.f_rho_r[0], self.f_rho_r[1], self.fast_H)
+            e.step_forces(dt)
+        self.stats["steps"] += 1
+
+
 class _NullCtx:
     def __enter__(self):
         return self
@@ -341,11 +439,17 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     del pos, vel, ids
     driver.rebalance()
 
-    def run(steps, rebalance_every=50):
+    def run(steps, rebalance_every=100):
+        # General (synchronous, all-to-all) step right after every change of cuts; the sync-free
+        # step with fixed-size neighbour messages in between.
         for k in range(steps):
-            if world > 1 and k and k % rebalance_every == 0:
-                driver.rebalance()
-            driver.step(s.dt)
+            if k % rebalance_every == 0:
+                if world > 1:
+                    driver.rebalance()
+                driver.step(s.dt)
+                driver.setup_fast(driver.suggest_halo_rows())
+            else:
+                driver.step_fast(s.dt)
 
     run(args.settle)
     if world > 1:
@@ -370,7 +474,8 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     sim.sync()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
-    owned = torch.tensor([driver.e.owned], dtype=torch.int64, device=f"cuda:{local}")
+    st = sim.stats()
+    owned = torch.tensor([int(st.count)], dtype=torch.int64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         owned_all = [torch.zeros_like(owned) for _ in range(world)]
@@ -379,7 +484,6 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     else:
         owned_list = [int(owned.item())]
     clk = clocks.stop()
-    st = sim.stats()
     total_s = float(ms.item()) * 1e-3
     value = n_total * args.steps / total_s
     if rank == 0:
@@ -392,7 +496,10 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
                        "h": scene["h"], "dt": s.dt, "lattice": [nx, ny, nz], "settle_steps": args.settle,
                        "l2": "state per GPU (>= 8 M particles, ~1 GB touched per step) is larger than the 126 MB L2; "
                              "L2 flushed once before the timed region",
-                       "decomposition": "x slabs, all-to-all migration + 1-cell ghost halo + density halo per step (NCCL)",
+                       "decomposition": "x slabs; per step: migrants, 1-cell ghost halo and halo densities as fixed-size "
+                                        "NCCL send/recv to the adjacent ranks with device-resident counts (no host sync); "
+                                        "general all-to-all step + rebalance every 100 steps",
+                       "halo_message_rows": getattr(driver, "fast_H", None),
                        "rank0_mean_density": st.mean_density, "rank0_grid_dim": list(st.grid_dim),
                        "migrated_rows_rank0": driver.stats["migrated_rows"], "halo_rows_rank0": driver.stats["halo_rows"],
                        "phase_ms_per_step_rank0": {k: 1e3 * v / max(driver.stats["steps"], 1) for k, v in driver.phase_s.items()}},
