@@ -294,6 +294,9 @@ def run_multi_gpu(args):
 
 
 def main():
+    # NCCL prints its version banner to stdout at VERSION/INFO level; keep stdout to the one JSON line.
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN") and not os.environ.get("SPH_KEEP_NCCL_DEBUG"):
+        os.environ.pop("NCCL_DEBUG")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
@@ -305,6 +308,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak-base", action="store_true", help="skip the single-GPU run of the per-GPU workload at N>1")
     ap.add_argument("--workload", default="auto", choices=["auto", "dam-break-1M", "weak"],
                     help="auto: config 1 at N=1, config 3 (weak scaling, 8 M particles per GPU) at N>1")
     args = ap.parse_args()

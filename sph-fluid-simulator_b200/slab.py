@@ -23,6 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 
 import numpy as np
 import torch
@@ -366,17 +367,25 @@ class SlabDriver:
         lo_prev = c[r - 1] if r > 0 else INT_MIN
         hi_next = c[r + 2] if r < w - 1 else INT_MAX
         with self._in_stream():
+            self._mark(None)
             e.fast_begin(lo, hi, lo_prev, hi_next, self.fast_M, self.f_mig_s[0], self.f_mig_s[1])
+            self._mark("f_begin")
             self._p2p(self.f_mig_s, self.f_mig_r)
+            self._mark("f_migrate_exchange")
             e.fast_arrivals(self.f_mig_r[0], self.f_mig_r[1], self.fast_M)
             e.fast_halo(lo, hi, self.fast_H, self.f_halo_s[0], self.f_halo_s[1])
+            self._mark("f_halo_pack")
             self._p2p(self.f_halo_s, self.f_halo_r)
+            self._mark("f_halo_exchange")
             e.fast_ghosts(self.f_halo_r[0], self.f_halo_r[1], self.fast_H)
             e.step_density()
+            self._mark("f_density")
             e.fast_pack_density(self.fast_H, self.f_rho_s[0], self.f_rho_s[1])
             self._p2p(self.f_rho_s, self.f_rho_r)
             e.fast_set_ghost_density(self.f_rho_r[0], self.f_rho_r[1], self.fast_H)
+            self._mark("f_rho_exchange")
             e.step_forces(dt)
+            self._mark("f_forces")
         self.stats["steps"] += 1
 
 
@@ -430,6 +439,37 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     scene = scene_fn(world)
     s = S.scaled_settings(scene["h"])
     nx, ny, nz = scene["dims"]
+
+    # Weak-scaling base: the same per-GPU workload (one 61 x 256 x 512 block) on ONE GPU, measured in
+    # this job on rank 0 with the same settle / warm-up / step counts, so that the scaling series has
+    # a like-for-like N = 1 point (bench.py --gpus 1 runs config 1, the 1 M dam break, instead).
+    base = None
+    if world > 1 and not getattr(args, "no_weak_base", False):
+        if rank == 0:
+            b = scene_fn(1)
+            bx, by, bz = b["dims"]
+            bpos, bvel, bids = S.scene_block_slice(bx, by, bz, b["sep"], b["origin"], b["h"], b["seed"], 0, bx)
+            bdrv, bsim = make_gpu_driver(s, int(bpos.shape[0] * 1.25) + (1 << 20), local, 0, 1)
+            bsim.upload(bpos, bvel, bids)
+            for _ in range(args.settle + max(args.warmup, 3)):
+                bdrv.step(s.dt)
+            bsim.sync()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(bdrv.e.stream):
+                t0.record(bdrv.e.stream)
+            for _ in range(args.steps):
+                bdrv.step(s.dt)
+            with torch.cuda.stream(bdrv.e.stream):
+                t1.record(bdrv.e.stream)
+            bsim.sync()
+            bms = t0.elapsed_time(t1) / args.steps
+            base = {"n_gpus": 1, "particles": int(bpos.shape[0]), "ms_per_step": bms,
+                    "value": bpos.shape[0] / (bms * 1e-3), "workload": b["name"]}
+            bsim.close()
+            del bpos, bvel, bids, bdrv, bsim
+            torch.cuda.empty_cache()
+        dist.barrier()
+
     per = nx // world
     i0, i1 = rank * per, (rank + 1) * per if rank < world - 1 else nx
     pos, vel, ids = S.scene_block_slice(nx, ny, nz, scene["sep"], scene["origin"], scene["h"], scene["seed"], i0, i1)
@@ -484,6 +524,9 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     else:
         owned_list = [int(owned.item())]
     clk = clocks.stop()
+    if driver.profile:
+        print(f"[rank {rank}] phase ms/step:", {k: round(1e3 * v / max(driver.stats['steps'], 1), 3) for k, v in driver.phase_s.items()},
+              file=sys.stderr, flush=True)
     total_s = float(ms.item()) * 1e-3
     value = n_total * args.steps / total_s
     if rank == 0:
@@ -500,6 +543,7 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
                                         "NCCL send/recv to the adjacent ranks with device-resident counts (no host sync); "
                                         "general all-to-all step + rebalance every 100 steps",
                        "halo_message_rows": getattr(driver, "fast_H", None),
+                       "single_gpu_same_workload": base,
                        "rank0_mean_density": st.mean_density, "rank0_grid_dim": list(st.grid_dim),
                        "migrated_rows_rank0": driver.stats["migrated_rows"], "halo_rows_rank0": driver.stats["halo_rows"],
                        "phase_ms_per_step_rank0": {k: 1e3 * v / max(driver.stats["steps"], 1) for k, v in driver.phase_s.items()}},

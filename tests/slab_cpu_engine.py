@@ -134,6 +134,77 @@ class CpuOracleEngine:
         self.force = np.zeros((n, 3), np.float32)
         self.force[order] = force
 
+    # -- sync-free path (same contract as slab.GpuEngine.fast_*): fixed-size messages whose unused
+    #    rows carry the dropped-row pattern 0xFFFFFFFF in every word --------------------------------
+    DROP = np.uint32(0xFFFFFFFF)
+
+    def _fixed_rows(self, sel, cap):
+        assert len(sel) <= cap, "message overflow"
+        out = np.full((cap, 8), np.float32(np.nan))
+        out = out.view(np.uint32)
+        out[:] = self.DROP
+        if len(sel):
+            out[:len(sel)] = self._rows(sel).numpy().view(np.uint32)
+        return torch.from_numpy(out.view(np.float32))
+
+    def fast_begin(self, lo, hi, lo_prev, hi_next, cap, send_l, send_r):
+        live = (self.idw & GHOST) == 0
+        cx = self.cell_x()
+        go_l = live & (cx < lo) if send_l is not None else np.zeros(len(cx), bool)
+        go_r = live & (cx >= hi) if send_r is not None else np.zeros(len(cx), bool)
+        assert not (go_l & (cx < lo_prev)).any() and not (go_r & (cx >= hi_next)).any(), "non-adjacent migrant"
+        if send_l is not None:
+            send_l.copy_(self._fixed_rows(np.nonzero(go_l)[0], cap))
+        if send_r is not None:
+            send_r.copy_(self._fixed_rows(np.nonzero(go_r)[0], cap))
+        keep = live & ~go_l & ~go_r
+        self.pos, self.vel, self.idw = self.pos[keep], self.vel[keep], self.idw[keep]
+
+    def _append_fixed(self, msg, ghost_side):
+        rows = msg.numpy().view(np.uint32)
+        valid = rows[:, 3] != self.DROP
+        self.append(torch.from_numpy(rows[valid].view(np.float32).copy()), 0 if ghost_side is None else ghost_side + 1)
+
+    def fast_arrivals(self, recv_l, recv_r, cap):
+        for m in (recv_l, recv_r):
+            if m is not None:
+                self._append_fixed(m, None)
+
+    def fast_halo(self, lo, hi, cap, send_l, send_r):
+        live = (self.idw & GHOST) == 0
+        cx = self.cell_x()
+        for side, (buf, cell) in enumerate(((send_l, lo), (send_r, hi - 1))):
+            if buf is None:
+                self.halo_rows[side] = np.zeros(0, np.int64)
+                continue
+            sel = np.nonzero(live & (cx == cell))[0]
+            self.halo_rows[side] = sel
+            buf.copy_(self._fixed_rows(sel, cap))
+
+    def fast_ghosts(self, recv_l, recv_r, cap):
+        self.ghost_batch = [(len(self.pos), 0), (len(self.pos), 0)]
+        for side, m in enumerate((recv_l, recv_r)):
+            if m is not None:
+                self._append_fixed(m, side)
+
+    def fast_pack_density(self, cap, send_l, send_r):
+        for side, buf in enumerate((send_l, send_r)):
+            if buf is None:
+                continue
+            out = np.full(cap, self.DROP, np.uint32)
+            sel = self.halo_rows[side]
+            out[:len(sel)] = self.rho[sel].view(np.uint32)
+            buf.copy_(torch.from_numpy(out.view(np.float32)))
+
+    def fast_set_ghost_density(self, recv_l, recv_r, cap):
+        for side, m in enumerate((recv_l, recv_r)):
+            if m is None:
+                continue
+            first, n = self.ghost_batch[side]
+            vals = m.numpy()
+            assert (vals[:n].view(np.uint32) != self.DROP).all() and (vals[n:].view(np.uint32) == self.DROP).all()
+            self.rho[first:first + n] = vals[:n]
+
     def xcell_histogram(self, x_lo, nbins):
         live = (self.idw & GHOST) == 0
         b = np.clip(self.cell_x()[live] - x_lo, 0, nbins - 1)

@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, steps, rebalance_every, out_dir):
+def _worker(rank, world, port, steps, rebalance_every, out_dir, fast=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -41,10 +41,16 @@ def _worker(rank, world, port, steps, rebalance_every, out_dir):
     eng.upload(pos[mine], vel[mine], ids[mine])
     drv = slab.SlabDriver(eng, rank, world, x_lo=-60, nbins=121)
     drv.rebalance()
-    for k in range(steps):
-        if rebalance_every and k and k % rebalance_every == 0:
-            drv.rebalance()
-        drv.step(float(g["dt"]))
+    if fast:
+        drv.step(float(g["dt"]))  # general path delivers the round-robin rows to their owners
+        drv.setup_fast(drv.suggest_halo_rows())
+        for k in range(1, steps):
+            drv.step_fast(float(g["dt"]))
+    else:
+        for k in range(steps):
+            if rebalance_every and k and k % rebalance_every == 0:
+                drv.rebalance()
+            drv.step(float(g["dt"]))
     st = eng.owned_state()
     cx = eng.cell_x()[(eng.idw & 0x80000000) == 0]
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), cuts=np.array(drv.cuts, np.int64), cell_x=cx,
@@ -52,9 +58,9 @@ def _worker(rank, world, port, steps, rebalance_every, out_dir):
     dist.destroy_process_group()
 
 
-def _run(world, steps, rebalance_every=0):
+def _run(world, steps, rebalance_every=0, fast=False):
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, _free_port(), steps, rebalance_every, d), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), steps, rebalance_every, d, fast), nprocs=world, join=True)
         return [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
 
 
@@ -91,6 +97,19 @@ def test_slab_driver_matches_undivided_oracle(oracle, world):
     assert sum(int(d["migrated"]) for d in ranks) > len(want["pos"]) // 3
     # balanced cuts: no rank holds more than ~1.5x its share
     assert max(len(d["id"]) for d in ranks) < 1.5 * len(want["pos"]) / world + 200
+
+
+def test_sync_free_step_matches_undivided_oracle(oracle):
+    """The fixed-size-message path (step_fast) after one general step, world_size 2."""
+    ranks = _run(2, 4, fast=True)
+    want = _oracle_reference(oracle, 4)
+    ids = np.concatenate([r["id"] for r in ranks])
+    assert np.array_equal(np.sort(ids), np.arange(len(want["pos"]), dtype=np.uint32))
+    for d in ranks:
+        i = d["id"]
+        assert np.array_equal(d["hash"], want["hash"][i])
+        assert (np.abs(d["density"] - want["density"][i]) / want["density"][i]).max() < 1e-5
+        assert np.abs(d["pos"] - want["pos"][i]).max() < 2e-5
 
 
 def test_rebalance_moves_ownership(oracle):
