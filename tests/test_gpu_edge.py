@@ -1,0 +1,217 @@
+"""GPU: edge cases and size-independent properties of the CUDA path (through the C-ABI).
+
+Edge cases the reference code has (it has no tests of its own): empty and tiny systems, particles
+that start outside the walls, negative coordinates and the double-width cell 0, coincident particles
+(NaN forces, exactly as the reference produces them), a grid that has to be clipped, capacity and
+state errors. Properties at the full 1 M size of BASELINE.json config 1: determinism, independence
+of the upload order, sortedness, id conservation, hash-table consistency.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, assert_bit_equal, assert_fields_close, by_id
+
+pytestmark = pytest.mark.gpu
+
+
+def step_both(sph, oracle, s, pos, vel, steps=1):
+    sim = sph.Sim(s, capacity=max(len(pos), 1))
+    sim.upload(pos, vel)
+    sim.step(steps)
+    got = sim.download(sph.ORDER_ID)
+    sim.close()
+    os_ = oracle.settings(s.as_tuple7())
+    p, v, ids = pos, vel, np.arange(len(pos), dtype=np.uint32)
+    for _ in range(steps):
+        o = oracle.step(os_, s.dt, p, v, ids)
+        p, v, ids = o["pos"], o["vel"], o["id"]
+    return got, by_id(o)
+
+
+def test_empty_and_tiny_systems(sph, oracle):
+    s = sph.default_settings()
+    sim = sph.Sim(s, capacity=8)
+    sim.upload(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    sim.step(3)
+    assert sim.count == 0 and sim.download(sph.ORDER_DEVICE, fields=("pos",))["pos"].shape == (0, 3)
+    sim.close()
+    for n in (1, 2, 3):
+        pos = np.array([[0.0, 1.0, 0.0], [0.05, 1.0, 0.0], [0.0, 1.1, 0.05]], np.float32)[:n]
+        vel = np.zeros((n, 3), np.float32)
+        got, want = step_both(sph, oracle, s, pos, vel, steps=2)
+        assert np.array_equal(got["hash"], want["hash"])
+        assert_fields_close(got, want, f"n={n}")
+
+
+def test_particles_outside_walls_negative_coordinates_and_cell_zero(sph, oracle):
+    """The shipped cube overflows the box for widths >= 60; x,z < 0 truncate toward zero so cell 0
+    spans (-h, h); a floor-penetrating start is mirrored (src/sph.cpp:153-176)."""
+    rng = np.random.default_rng(11)
+    s = sph.default_settings()
+    pos = np.concatenate([
+        rng.uniform([-12, -1, -12], [12, 6, 12], (3000, 3)),       # beyond every wall and below the floor
+        rng.uniform([-0.16, 0.1, -0.16], [0.16, 0.5, 0.16], (600, 3)),  # straddling cell 0 on x and z
+    ]).astype(np.float32)
+    vel = rng.normal(0, 1.0, pos.shape).astype(np.float32)
+    got, want = step_both(sph, oracle, s, pos, vel, steps=1)
+    assert np.array_equal(got["hash"], want["hash"])
+    assert_fields_close(got, want, "outside walls")
+    assert (got["pos"][:, 1] >= s.h - 1e-6).all(), "floor reflection"
+
+
+def test_coincident_particles_give_nan_like_the_reference(sph, oracle):
+    s = sph.default_settings()
+    pos = np.array([[0.5, 1.0, 0.5], [0.5, 1.0, 0.5], [0.55, 1.0, 0.5], [3.0, 2.0, 3.0]], np.float32)
+    vel = np.zeros_like(pos)
+    got, want = step_both(sph, oracle, s, pos, vel)
+    assert np.isnan(want["force"][:2]).all(), "normalize(0) in the reference (src/sph.cpp:111)"
+    assert np.isnan(got["force"][:2]).all() and np.isnan(got["pos"][:2]).all()
+    assert np.array_equal(np.isnan(got["force"]), np.isnan(want["force"]))
+    ok = ~np.isnan(want["pos"]).any(axis=1)
+    assert np.abs(got["pos"][ok] - want["pos"][ok]).max() < 1e-5
+    assert np.array_equal(got["density"].view(np.uint32), want["density"].view(np.uint32)) or \
+        np.abs(got["density"] - want["density"]).max() < 1e-4
+
+
+def test_grid_clipping_keeps_results_exact():
+    """With a tiny dense-grid allocation the box is clipped and outliers are clamped into the edge
+    layer: candidates become a superset, results must not change. Runs in a subprocess because the
+    allocation is fixed at sph_create from SPH_B200_MAX_CELLS."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import sph_b200 as S
+from conftest import load_golden
+g = load_golden("cube20_step200.npz")
+s = S.default_settings()
+pos, vel = g["pos0"].copy(), g["vel0"].copy()
+pos[:40, 1] += np.linspace(50, 4000, 40).astype(np.float32)   # a few particles far up: y has no ceiling
+sim = S.Sim(s, capacity=len(pos)); sim.upload(pos, vel); sim.step(2)
+out = sim.download(S.ORDER_ID); st = sim.stats()
+np.savez(sys.argv[1], clamped=st.clamped, cells=st.grid_cells, **out)
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        outs = []
+        for cells in ("67108864", "20000"):  # room for the whole 22 x 26 700 x 22 box / far too small
+            env = dict(os.environ)
+            env["SPH_B200_MAX_CELLS"] = cells
+            f = os.path.join(d, f"o{cells}.npz")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=env)
+            outs.append(dict(np.load(f)))
+    full, clipped = outs
+    # 20 000 cells clip all three axes of the 39 x 26 669 x 39 box: thousands of particles are clamped
+    assert int(full["clamped"]) == 0 and int(clipped["clamped"]) > 1000 and int(clipped["cells"]) <= 20000
+    assert np.array_equal(clipped["hash"], full["hash"])
+    # Same neighbour sets, but merged edge cells change the summation order: tolerance, not bits.
+    assert (np.abs(clipped["density"] - full["density"]) / full["density"]).max() < 1e-6
+    assert_fields_close(clipped, full, "clipped grid")
+
+
+def test_errors_are_reported_not_thrown(sph):
+    s = sph.default_settings()
+    sim = sph.Sim(s, capacity=10)
+    lib = sph.load_library()
+    with pytest.raises(sph.SphError) as e:
+        sim.step(1)
+    assert e.value.code == 3  # SPH_ERR_STATE: step before upload
+    with pytest.raises(sph.SphError) as e:
+        sim.upload(np.zeros((11, 3), np.float32), np.zeros((11, 3), np.float32))
+    assert e.value.code == 4  # SPH_ERR_CAPACITY
+    sim.upload(np.random.default_rng(0).uniform(0.2, 1, (10, 3)).astype(np.float32), np.zeros((10, 3), np.float32))
+    with pytest.raises(sph.SphError):
+        sim.download(sph.ORDER_ID, fields=("force",))  # undefined before the first step
+    sim.step(1)
+    sim.upload(np.zeros((4, 3), np.float32) + 0.5, np.zeros((4, 3), np.float32), ids=np.array([7, 8, 9, 10], np.uint32))
+    sim.step(1)
+    with pytest.raises(sph.SphError):
+        sim.download(sph.ORDER_ID)  # ids are not 0..n-1
+    assert sim.download(sph.ORDER_DEVICE)["id"].tolist() == [7, 8, 9, 10]
+    out = C.c_void_p()
+    assert lib.sph_create(C.byref(s), 10, 99, C.byref(out)) != 0 and b"device" in lib.sph_last_error(None)
+    sim.close()
+
+
+def test_settings_change_and_reupload(sph, oracle):
+    s = sph.default_settings()
+    pos, vel = sph.scene_cube(8, s.h)
+    sim = sph.Sim(s, capacity=2 * len(pos))
+    sim.upload(pos, vel)
+    sim.step(5)
+    s2 = sph.default_settings(viscosity=3.5, h=0.2, gas_constant=2.0)
+    sim.set_settings(s2)
+    cur = sim.download(sph.ORDER_ID, fields=("pos", "vel"))
+    sim.step(1)
+    got = sim.download(sph.ORDER_ID)
+    want = by_id(oracle.step(oracle.settings(s2.as_tuple7()), s2.dt, cur["pos"], cur["vel"]))
+    assert np.array_equal(got["hash"], want["hash"])
+    assert_fields_close(got, want, "after set_settings", gas_constant=2.0)
+    sim.close()
+
+
+@pytest.fixture(scope="module")
+def million(sph):
+    """BASELINE.json config 1: the 1 003 520-particle dam break, settled 200 steps."""
+    h = 0.075
+    s = sph.scaled_settings(h)
+    sep = h * 16.0 / 15.0
+    pos, vel = sph.scene_block(64, 80, 196, sep, ((h - 8.0) + sep, h * 5.0 / 3.0, -98 * sep), h, 1024)
+    sim = sph.Sim(s, capacity=len(pos))
+    sim.upload(pos, vel)
+    sim.step(200)
+    state = sim.download(sph.ORDER_ID, fields=("pos", "vel"))
+    sim.close()
+    return s, state
+
+
+def test_full_size_determinism_and_upload_order_independence(sph, million):
+    s, st = million
+    n = len(st["pos"])
+    perm = np.random.default_rng(5).permutation(n)
+    outs = []
+    for order in (None, None, perm):
+        sim = sph.Sim(s, capacity=n)
+        if order is None:
+            sim.upload(st["pos"], st["vel"])
+        else:
+            sim.upload(st["pos"][order], st["vel"][order], ids=order.astype(np.uint32))
+        sim.step(3)
+        outs.append(sim.download(sph.ORDER_ID))
+        sim.close()
+    for k in ("pos", "vel", "force", "density"):
+        assert_bit_equal(outs[1][k], outs[0][k], f"run-to-run {k}")
+        assert_bit_equal(outs[2][k], outs[0][k], f"permuted upload {k}")  # cells are ordered by particle id
+
+
+def test_full_size_sortedness_ids_and_hash_table(sph, oracle, million):
+    s, st = million
+    n = len(st["pos"])
+    sim = sph.Sim(s, capacity=n)
+    sim.upload(st["pos"], st["vel"])
+    sim.step(1)
+    dev = sim.download(sph.ORDER_DEVICE, fields=("id", "hash", "density"))
+    table = sim.hash_table()
+    h16 = sim.download(sph.ORDER_HASH16, fields=("hash", "id"))
+    grid = sim.stats()
+    sim.close()
+    # every particle exactly once
+    assert np.array_equal(np.sort(dev["id"]), np.arange(n, dtype=np.uint32))
+    # start-of-step hashes are the oracle's, bit for bit, for all 1 M particles
+    want_hash = oracle.hashes(st["pos"], s.h)
+    assert np.array_equal(dev["hash"], want_hash[dev["id"]])
+    # device order is sorted by dense-grid cell (x slowest, z, y fastest) of the start-of-step position
+    cells = np.array([np.trunc(st["pos"][dev["id"], a] / np.float32(s.h)) for a in range(3)], np.int64)
+    ox, oy, oz = grid.grid_origin
+    nx, ny, nz = grid.grid_dim
+    lin = ((cells[0] - ox) * nz + (cells[2] - oz)) * ny + (cells[1] - oy)
+    assert (np.diff(lin) >= 0).all(), "rows are not cell-sorted"
+    # the reference's hash -> first-index table, rebuilt from the hash16-ordered read-out
+    assert (np.diff(h16["hash"].astype(np.int64)) >= 0).all()
+    assert np.array_equal(table, oracle.neighbor_table(h16["hash"]))
+    assert int((table != 0xFFFFFFFF).sum()) == len(np.unique(want_hash)) and (table[65536:] == 0xFFFFFFFF).all()
+    assert np.isfinite(dev["density"]).all() and dev["density"].min() >= 9.28
