@@ -58,6 +58,16 @@ def weak_scaling_block(g):
     return dict(name=f"weak-scaling-8M-per-gpu-x{g}", h=h, sep=sep, dims=(nx, ny, nz), origin=origin, seed=1024)
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture of this workload
+    (profiles/r01_traffic.json, written by tools/ncu_traffic.py), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(kernel)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -252,7 +262,7 @@ def run_single_gpu(args):
     dom_name = {"forces": "k_forces_integrate", "density": "k_density", "grid": "grid build (5 kernels)", "integrate": "-"}[dominant]
     achieved = pass_bytes[dominant] * n / (passes[dominant] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": measured_traffic(dom_name), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": pass_bytes[dominant] * n,
                 "launch_ms": passes[dominant], "pass_ms": {k: passes[k] for k in pass_bytes},
                 "step_achieved_gbs": B_ALG_STEP * value / 1e9, "step_frac": B_ALG_STEP * value / 1e9 / peak}

@@ -277,6 +277,24 @@ int sph_slab_fast_ghosts(sph_handle *h, const void *dev_recv_left, const void *d
 int sph_slab_fast_pack_density(sph_handle *h, uint64_t cap_rows, void *dev_send_left, void *dev_send_right);
 int sph_slab_fast_set_ghost_density(sph_handle *h, const void *dev_recv_left, const void *dev_recv_right, uint64_t cap_rows);
 
+
+/* Peer-memory variant of the sync-free step (one box, NVLink/NVSwitch): instead of packing into a
+ * send buffer and handing it to NCCL, the pack kernels store rows straight into the adjacent
+ * rank's mailbox (a device allocation exported with CUDA IPC), a one-thread kernel publishes the
+ * row count and raises an epoch flag in the peer's memory, and the receiving stream spins on its
+ * own flag before appending. No collective library is involved in the step at all.
+ * Setup: every rank calls sph_slab_p2p_create (64-byte IPC handle out), the handles are exchanged by
+ * the caller, then sph_slab_p2p_connect(side 0 = left neighbour, 1 = right) for each neighbour.
+ * Step: p2p_begin -> p2p_arrivals -> p2p_halo -> p2p_ghosts -> sph_slab_step_density ->
+ * p2p_density -> sph_slab_step_forces; all ranks must step in lockstep. */
+int sph_slab_p2p_create(sph_handle *h, uint64_t halo_rows, uint64_t migrant_rows, void *ipc_handle_out64);
+int sph_slab_p2p_connect(sph_handle *h, int side, const void *peer_ipc_handle64);
+int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next);
+int sph_slab_p2p_arrivals(sph_handle *h);
+int sph_slab_p2p_halo(sph_handle *h, int32_t lo, int32_t hi);
+int sph_slab_p2p_ghosts(sph_handle *h);
+int sph_slab_p2p_density(sph_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,6 +60,12 @@ struct sph_handle {
     uint32_t *pinned_rows = nullptr;  // [0] rows surviving the last build, [1] slab violation bits
     cudaEvent_t ev_rows = nullptr;
     uint64_t fast_halo_cap = 0;
+    // peer-memory path
+    char *mailbox = nullptr;           // local mailbox (IPC-exported)
+    char *peer_mailbox[2] = {nullptr, nullptr};  // mapped mailboxes of the left / right neighbour
+    P2PLayout p2p{};
+    uint64_t p2p_H = 0, p2p_M = 0;
+    uint32_t p2p_epoch = 0;
     int forces_cfg = 0, density_cfg = 0;
     unsigned long long *slab_counts = nullptr;  // SLAB_MAX_RANKS counters + cursors
     uint32_t *cells = nullptr;
@@ -192,6 +198,7 @@ int resolve_rows(sph_handle *h)
                     (err & SLAB_ERR_MIGRANT_OVERFLOW) ? " migrant message overflow" : "",
                     (err & SLAB_ERR_HALO_OVERFLOW) ? " halo message overflow" : "",
                     (err & SLAB_ERR_NOT_ADJACENT) ? " a particle left for a non-adjacent slab" : "");
+    // (SLAB_ERR_P2P_TIMEOUT is reported through the same bits: a neighbour never raised its flag)
     return SPH_OK;
 }
 
@@ -515,6 +522,9 @@ int sph_destroy(sph_handle *h)
     cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
     cudaFree(h->stats_acc); cudaFree(h->scratch);
+    for (int k = 0; k < 2; ++k)
+        if (h->peer_mailbox[k]) cudaIpcCloseMemHandle(h->peer_mailbox[k]);
+    cudaFree(h->mailbox);
     if (h->pinned_rows) cudaFreeHost(h->pinned_rows);
     if (h->ev_rows) cudaEventDestroy(h->ev_rows);
     for (auto &pe : h->ev_pool)
@@ -1263,6 +1273,198 @@ int sph_slab_fast_set_ghost_density(sph_handle *h, const void *dev_recv_left, co
             h->vel[h->cur], h->inverse, (uint32_t)h->ghost_first[side], (uint32_t)cap_rows, (const float *)src[side]);
         CK_LAUNCH();
         ++h->launches;
+    }
+    return SPH_OK;
+}
+
+// ---- peer-memory slab path: pack kernels store into the neighbours' mailboxes over NVLink ----------
+
+int sph_slab_p2p_create(sph_handle *h, uint64_t halo_rows, uint64_t migrant_rows, void *ipc_handle_out64)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (!ipc_handle_out64 || halo_rows == 0 || migrant_rows == 0) return fail(h, SPH_ERR_INVALID, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is exchanged as 64 bytes");
+    if (h->mailbox) return fail(h, SPH_ERR_STATE, "mailbox already created");
+    P2PLayout L{};
+    unsigned long long off = 0;
+    auto take = [&](unsigned long long bytes) { const unsigned long long o = off; off += (bytes + 255) / 256 * 256; return o; };
+    for (int s2 = 0; s2 < 2; ++s2)
+        for (int b = 0; b < 2; ++b) {
+            L.mig[s2][b] = take(migrant_rows * 32);
+            L.halo[s2][b] = take(halo_rows * 32);
+            L.rho[s2][b] = take(halo_rows * 4);
+        }
+    for (int s2 = 0; s2 < 2; ++s2)
+        for (int t = 0; t < 3; ++t) {
+            for (int b = 0; b < 2; ++b) L.count[s2][t][b] = take(4);
+            L.flag[s2][t] = take(4);
+        }
+    L.bytes = off;
+    CK(cudaMalloc(&h->mailbox, L.bytes));
+    CK(cudaMemset(h->mailbox, 0, L.bytes));
+    cudaIpcMemHandle_t ih;
+    CK(cudaIpcGetMemHandle(&ih, h->mailbox));
+    std::memcpy(ipc_handle_out64, &ih, 64);
+    h->p2p = L;
+    h->p2p_H = halo_rows;
+    h->p2p_M = migrant_rows;
+    h->p2p_epoch = 0;
+    return SPH_OK;
+}
+
+int sph_slab_p2p_connect(sph_handle *h, int side, const void *peer_ipc_handle64)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (side < 0 || side > 1 || !peer_ipc_handle64) return fail(h, SPH_ERR_INVALID, "bad arguments");
+    if (!h->mailbox) return fail(h, SPH_ERR_STATE, "create the local mailbox first");
+    cudaIpcMemHandle_t ih;
+    std::memcpy(&ih, peer_ipc_handle64, 64);
+    void *ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_mailbox[side] = (char *)ptr;
+    return SPH_OK;
+}
+
+namespace {
+// Mailbox side indices: messages that arrive FROM my left neighbour land in my side 0; so when I send
+// to my LEFT neighbour I write into ITS side 1 (I am its right neighbour), and vice versa.
+inline char *peer_slot(sph_handle *h, int to_side, unsigned long long off) { return h->peer_mailbox[to_side] + off; }
+}  // namespace
+
+int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (!h->have_state || !h->slab_mode || !h->mailbox) return fail(h, SPH_ERR_STATE, "slab mode with a mailbox required");
+    cudaStream_t s = h->stream;
+    ++h->p2p_epoch;
+    const int b = h->p2p_epoch & 1;
+    const P2PLayout &L = h->p2p;
+    unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
+    CK(cudaMemsetAsync(cur, 0, 4 * sizeof(unsigned long long), s));
+    CK(cudaMemsetAsync(&h->ctr->aux[3], 0, sizeof(uint32_t), s));
+    float4 *dst[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; ++side)
+        if (h->peer_mailbox[side]) dst[side] = (float4 *)peer_slot(h, side, L.mig[side ^ 1][b]);
+    if (h->n) {
+        k_slab_fast_begin<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dst[0] ? lo : -0x7fffffff - 1, dst[1] ? hi : 0x7fffffff,
+            lo_prev, hi_next, (uint32_t)h->p2p_M, dst[0], dst[1], cur, &h->ctr->aux[3]);
+        CK_LAUNCH();
+    }
+    for (int side = 0; side < 2; ++side)
+        if (h->peer_mailbox[side]) {
+            k_p2p_publish<<<1, 32, 0, s>>>((uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_MIG][b]), cur + side,
+                                          (uint32_t)h->p2p_M, (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][P2P_MIG]),
+                                          h->p2p_epoch);
+            CK_LAUNCH();
+        }
+    h->slab_fast = true;
+    h->n_ghost = 0;
+    h->ghost_n[0] = h->ghost_n[1] = 0;
+    h->have_step = false;
+    h->launches += 3;
+    return SPH_OK;
+}
+
+static int p2p_append(sph_handle *h, int type, bool ghost)
+{
+    const P2PLayout &L = h->p2p;
+    const int b = h->p2p_epoch & 1;
+    const uint64_t cap = type == P2P_MIG ? h->p2p_M : h->p2p_H;
+    const unsigned long long (*buf)[2] = type == P2P_MIG ? L.mig : L.halo;
+    for (int side = 0; side < 2; ++side) {
+        if (ghost) { h->ghost_first[side] = h->n; h->ghost_n[side] = h->peer_mailbox[side] ? cap : 0; }
+        if (!h->peer_mailbox[side]) continue;
+        if (h->n + cap > h->cap)
+            return fail(h, SPH_ERR_CAPACITY, "appending a %llu-row message to %llu rows exceeds capacity %llu",
+                        (unsigned long long)cap, (unsigned long long)h->n, (unsigned long long)h->cap);
+        k_p2p_wait<<<1, 32, 0, h->stream>>>((const uint32_t *)(h->mailbox + L.flag[side][type]), h->p2p_epoch, &h->ctr->aux[3]);
+        CK_LAUNCH();
+        k_slab_append_counted<<<blocks_for(cap, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            (const float4 *)(h->mailbox + buf[side][b]), (const uint32_t *)(h->mailbox + L.count[side][type][b]),
+            (uint32_t)cap, (uint32_t)h->n, ghost, h->pos[h->cur], h->vel[h->cur]);
+        CK_LAUNCH();
+        h->n += cap;
+        h->launches += 2;
+    }
+    return SPH_OK;
+}
+
+int sph_slab_p2p_arrivals(sph_handle *h)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    return p2p_append(h, P2P_MIG, false);
+}
+
+int sph_slab_p2p_halo(sph_handle *h, int32_t lo, int32_t hi)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const P2PLayout &L = h->p2p;
+    const int b = h->p2p_epoch & 1;
+    unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
+    float4 *dst[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; ++side)
+        if (h->peer_mailbox[side]) dst[side] = (float4 *)peer_slot(h, side, L.halo[side ^ 1][b]);
+    if (h->n) {
+        k_slab_fast_halo<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dst[0] != nullptr, dst[1] != nullptr,
+            (uint32_t)h->p2p_H, dst[0], dst[1], h->halo_rows[0], h->halo_rows[1], cur, &h->ctr->aux[3]);
+        CK_LAUNCH();
+    }
+    for (int side = 0; side < 2; ++side)
+        if (h->peer_mailbox[side]) {
+            k_p2p_publish<<<1, 32, 0, s>>>((uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_HALO][b]), cur + 2 + side,
+                                          (uint32_t)h->p2p_H, (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][P2P_HALO]),
+                                          h->p2p_epoch);
+            CK_LAUNCH();
+        }
+    h->fast_halo_cap = h->p2p_H;
+    h->launches += 3;
+    return SPH_OK;
+}
+
+int sph_slab_p2p_ghosts(sph_handle *h)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    return p2p_append(h, P2P_HALO, true);
+}
+
+// Densities of my boundary rows into the neighbours' mailboxes, then the neighbours' into my ghosts.
+int sph_slab_p2p_density(sph_handle *h)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    cudaStream_t s = h->stream;
+    const P2PLayout &L = h->p2p;
+    const int b = h->p2p_epoch & 1;
+    const uint32_t cap = (uint32_t)h->p2p_H;
+    unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
+    for (int side = 0; side < 2; ++side) {
+        if (!h->peer_mailbox[side]) continue;
+        k_slab_fast_pack_density<<<blocks_for(cap, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+            h->vel[h->cur], h->inverse, h->halo_rows[side], cur + 2 + side, cap, (float *)peer_slot(h, side, L.rho[side ^ 1][b]));
+        CK_LAUNCH();
+        k_p2p_publish<<<1, 32, 0, s>>>((uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_RHO][b]), cur + 2 + side, cap,
+                                      (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][P2P_RHO]), h->p2p_epoch);
+        CK_LAUNCH();
+        h->launches += 2;
+    }
+    for (int side = 0; side < 2; ++side) {
+        if (!h->peer_mailbox[side] || h->ghost_n[side] == 0) continue;
+        k_p2p_wait<<<1, 32, 0, s>>>((const uint32_t *)(h->mailbox + L.flag[side][P2P_RHO]), h->p2p_epoch, &h->ctr->aux[3]);
+        CK_LAUNCH();
+        k_slab_set_ghost_density_counted<<<blocks_for(cap, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+            h->vel[h->cur], h->inverse, (uint32_t)h->ghost_first[side], (const uint32_t *)(h->mailbox + L.count[side][P2P_RHO][b]),
+            cap, (const float *)(h->mailbox + L.rho[side][b]));
+        CK_LAUNCH();
+        h->launches += 2;
     }
     return SPH_OK;
 }

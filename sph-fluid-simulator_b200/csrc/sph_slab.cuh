@@ -257,4 +257,80 @@ k_slab_xhist(const float4 *__restrict__ pos, uint32_t n, float h, int x_lo, uint
     atomicAdd(&hist[b], 1ull);
 }
 
+
+// ---- peer-memory path: the pack kernels store straight into the neighbour's mailbox over NVLink ----
+//
+// Every rank owns a mailbox (one device allocation, exported with cudaIpcGetMemHandle and mapped
+// by both neighbours). For each side it holds, double-buffered by step parity, a migrant message,
+// a halo message and a density message, plus per-message row counts and one epoch flag per
+// message type. The sender's pack kernel writes rows directly into the peer mailbox (no send
+// buffer, no NCCL kernel), a one-thread publish kernel then stores the row count, fences at system
+// scope and raises the peer's flag to the step epoch; the receiver's stream spins on its own flag
+// before it appends. Two buffers are enough: a sender reaches epoch e+2 only after it has waited
+// for the neighbour's epoch e+1 message, which the neighbour sent after consuming epoch e.
+constexpr uint32_t SLAB_ERR_P2P_TIMEOUT = 8u;
+
+struct P2PLayout {
+    unsigned long long mig[2][2], halo[2][2], rho[2][2];  // byte offsets [side][parity]
+    unsigned long long count[2][3][2];                     // uint32 [side][type][parity]
+    unsigned long long flag[2][3];                         // uint32 [side][type]
+    unsigned long long bytes;
+};
+enum { P2P_MIG = 0, P2P_HALO = 1, P2P_RHO = 2 };
+
+__global__ void k_p2p_publish(uint32_t *peer_count, const unsigned long long *local_cursor, uint32_t cap,
+                              uint32_t *peer_flag, uint32_t epoch)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long c = *local_cursor;
+    *peer_count = (uint32_t)(c < cap ? c : cap);
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(peer_flag) = epoch;
+}
+
+// Spin (one thread) until the local flag reaches the epoch; gives up after ~4 s and records it.
+__global__ void k_p2p_wait(const uint32_t *flag, uint32_t epoch, uint32_t *err)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const volatile uint32_t *f = flag;
+    const long long t0 = clock64();
+    while ((int)(*f - epoch) < 0) {
+        __nanosleep(200);
+        if (clock64() - t0 > 8000000000ll) {
+            atomicOr(err, SLAB_ERR_P2P_TIMEOUT);
+            break;
+        }
+    }
+    __threadfence_system();
+}
+
+// Append a counted message from the local mailbox into a fixed region of `cap` rows: rows past
+// the count become dropped rows.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_append_counted(const float4 *__restrict__ rows, const uint32_t *__restrict__ count, uint32_t cap, uint32_t first,
+                      bool ghost, float4 *__restrict__ pos, float4 *__restrict__ vel)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cap) return;
+    if (k >= *count) {
+        pos[first + k] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
+        return;
+    }
+    float4 p = rows[2 * k];
+    const float4 v = rows[2 * k + 1];
+    uint32_t w = __float_as_uint(p.w) & W_ID_MASK;
+    if (ghost) w |= W_GHOST;
+    p.w = __uint_as_float(w);
+    pos[first + k] = p;
+    vel[first + k] = v;
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_set_ghost_density_counted(float4 *__restrict__ vel, const uint32_t *__restrict__ inverse, uint32_t first,
+                                 const uint32_t *__restrict__ count, uint32_t cap, const float *__restrict__ in)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < cap && k < *count) vel[inverse[first + k]].w = in[k];
+}
+
 }  // namespace sphb

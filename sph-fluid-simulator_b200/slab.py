@@ -117,6 +117,26 @@ class GpuEngine:
     def sync(self):
         self.sim.sync()
 
+    # -- peer-memory path: no transport library in the step at all -----------------------------------
+    def p2p_create(self, halo_rows, migrant_rows) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._ck(self.lib.sph_slab_p2p_create(self.sim.handle, halo_rows, migrant_rows, buf))
+        return bytes(buf)
+
+    def p2p_connect(self, side, handle: bytes):
+        buf = (C.c_ubyte * 64)(*handle)
+        self._ck(self.lib.sph_slab_p2p_connect(self.sim.handle, side, buf))
+
+    def p2p_step(self, lo, hi, lo_prev, hi_next, dt):
+        h, L = self.sim.handle, self.lib
+        self._ck(L.sph_slab_p2p_begin(h, int(lo), int(hi), int(lo_prev), int(hi_next)))
+        self._ck(L.sph_slab_p2p_arrivals(h))
+        self._ck(L.sph_slab_p2p_halo(h, int(lo), int(hi)))
+        self._ck(L.sph_slab_p2p_ghosts(h))
+        self._ck(L.sph_slab_step_density(h))
+        self._ck(L.sph_slab_p2p_density(h))
+        self._ck(L.sph_slab_step_forces(h, C.c_float(dt)))
+
     # -- sync-free path: fixed-size messages, tensors may be None (no neighbour on that side) --------
     @staticmethod
     def _p(t):
@@ -338,6 +358,37 @@ class SlabDriver:
             worst = max(worst, int(hist[max(b - 2, 0):b + 2].max()))
         return int(max(4096, slack * worst))
 
+    # -- peer-memory step ------------------------------------------------------------------------
+    def setup_p2p(self, halo_rows: int, migrant_rows: int | None = None):
+        """Create the mailboxes and map the neighbours' (CUDA IPC). Collective; once per run."""
+        r, w = self.rank, self.world
+        mig = int(migrant_rows if migrant_rows is not None else max(4096, halo_rows // 8))
+        mine = self.e.p2p_create(int(halo_rows), mig)
+        t = torch.tensor(list(mine), dtype=torch.uint8)
+        if self.backend == "nccl":
+            t = t.to(self.e.device)
+        allh = [torch.empty_like(t) for _ in range(w)]
+        if w > 1:
+            dist.all_gather(allh, t, group=self.group)
+        else:
+            allh = [t]
+        if r > 0:
+            self.e.p2p_connect(0, bytes(allh[r - 1].cpu().tolist()))
+        if r < w - 1:
+            self.e.p2p_connect(1, bytes(allh[r + 1].cpu().tolist()))
+        if w > 1:
+            dist.barrier(group=self.group)
+        self.p2p_ready = True
+        self.fast_H = int(halo_rows)
+
+    def step_p2p(self, dt: float = 0.0):
+        """One step whose exchanges are stores into the neighbours' mailboxes: no collective calls,
+        no host synchronisation. All ranks must call it in lockstep; cuts must be unchanged since the
+        last general step()."""
+        r, w, c = self.rank, self.world, self.cuts
+        self.e.p2p_step(c[r], c[r + 1], c[r - 1] if r > 0 else INT_MIN, c[r + 2] if r < w - 1 else INT_MAX, dt)
+        self.stats["steps"] += 1
+
     def _p2p(self, send, recv):
         """Exchange fixed-size messages with the adjacent ranks (send/recv = [left, right])."""
         r, w = self.rank, self.world
@@ -479,15 +530,22 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     del pos, vel, ids
     driver.rebalance()
 
+    transport = os.environ.get("SPH_SLAB_TRANSPORT", "p2p")  # p2p (peer-memory mailboxes) | nccl | general
+
     def run(steps, rebalance_every=100):
-        # General (synchronous, all-to-all) step right after every change of cuts; the sync-free
-        # step with fixed-size neighbour messages in between.
+        # General (synchronous, all-to-all) step right after every change of cuts; in between, the
+        # sync-free step: stores into the neighbours' mailboxes (p2p) or fixed-size NCCL messages.
         for k in range(steps):
-            if k % rebalance_every == 0:
-                if world > 1:
+            if k % rebalance_every == 0 or transport == "general":
+                if world > 1 and k % rebalance_every == 0:
                     driver.rebalance()
                 driver.step(s.dt)
-                driver.setup_fast(driver.suggest_halo_rows())
+                if transport == "p2p" and not getattr(driver, "p2p_ready", False):
+                    driver.setup_p2p(2 * driver.suggest_halo_rows())
+                elif transport == "nccl":
+                    driver.setup_fast(driver.suggest_halo_rows())
+            elif transport == "p2p":
+                driver.step_p2p(s.dt)
             else:
                 driver.step_fast(s.dt)
 
@@ -539,9 +597,10 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
                        "h": scene["h"], "dt": s.dt, "lattice": [nx, ny, nz], "settle_steps": args.settle,
                        "l2": "state per GPU (>= 8 M particles, ~1 GB touched per step) is larger than the 126 MB L2; "
                              "L2 flushed once before the timed region",
-                       "decomposition": "x slabs; per step: migrants, 1-cell ghost halo and halo densities as fixed-size "
-                                        "NCCL send/recv to the adjacent ranks with device-resident counts (no host sync); "
-                                        "general all-to-all step + rebalance every 100 steps",
+                       "decomposition": "x slabs; per step: migrants, 1-cell ghost halo and halo densities go to the adjacent "
+                                        "ranks with device-resident counts and no host sync; transport = " + transport +
+                                        " (p2p: pack kernels store into the neighbour's CUDA-IPC mailbox over NVLink; "
+                                        "nccl: fixed-size send/recv); general all-to-all step + rebalance every 100 steps",
                        "halo_message_rows": getattr(driver, "fast_H", None),
                        "single_gpu_same_workload": base,
                        "rank0_mean_density": st.mean_density, "rank0_grid_dim": list(st.grid_dim),

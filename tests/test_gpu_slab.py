@@ -51,11 +51,16 @@ def _worker(rank, world, port, backend, steps, fast, out_dir):
     drv.rebalance()
     if fast:
         # first step through the general path (it delivers the scrambled rows to their owners),
-        # then the sync-free path with fixed-size messages
+        # then the sync-free path: fixed-size NCCL/gloo messages, or stores into peer mailboxes
         drv.step(s.dt)
-        drv.setup_fast(drv.suggest_halo_rows())
-        for k in range(1, steps):
-            drv.step_fast(s.dt)
+        if fast == "p2p":
+            drv.setup_p2p(drv.suggest_halo_rows())
+            for k in range(1, steps):
+                drv.step_p2p(s.dt)
+        else:
+            drv.setup_fast(drv.suggest_halo_rows())
+            for k in range(1, steps):
+                drv.step_fast(s.dt)
     else:
         for k in range(steps):
             if k == steps // 2:
@@ -95,7 +100,7 @@ def _compare(ranks, want, world):
         assert max(len(d["id"]) for d in ranks) < 1.6 * len(want["pos"]) / world
 
 
-@pytest.mark.parametrize("fast", [False, True], ids=["general", "syncfree"])
+@pytest.mark.parametrize("fast", [False, True, "p2p"], ids=["general", "syncfree", "peer-mailbox"])
 @pytest.mark.parametrize("world", [1, 2, 3])
 def test_slab_step_is_bit_identical_to_single_gpu_gloo(sph, world, fast):
     steps = 6
@@ -106,7 +111,7 @@ def test_slab_step_is_bit_identical_to_single_gpu_gloo(sph, world, fast):
     _compare(ranks, want, world)
 
 
-@pytest.mark.parametrize("fast", [False, True], ids=["general", "syncfree"])
+@pytest.mark.parametrize("fast", [False, True, "p2p"], ids=["general", "syncfree", "peer-mailbox"])
 def test_slab_step_over_nccl(sph, fast):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
