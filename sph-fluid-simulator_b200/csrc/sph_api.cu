@@ -60,6 +60,8 @@ struct sph_handle {
     uint32_t *pinned_rows = nullptr;  // [0] rows surviving the last build, [1] slab violation bits
     cudaEvent_t ev_rows = nullptr;
     uint64_t fast_halo_cap = 0;
+    bool have_bbox_from_integration = false;
+    int bbox_expand = 0;          // cells added around the box by the next grid plan
     // peer-memory path
     char *mailbox = nullptr;           // local mailbox (IPC-exported)
     char *peer_mailbox[2] = {nullptr, nullptr};  // mapped mailboxes of the left / right neighbour
@@ -232,7 +234,7 @@ int build_grid(sph_handle *h)
 {
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
-    k_plan_zero<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells, h->cells);
+    k_plan_zero<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
     CK_LAUNCH();
     k_cell_hist<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->pos[h->cur], n, h->P.h, h->gd, h->cells,
                                                                    h->cell_rank, h->ctr);
@@ -379,6 +381,7 @@ int after_upload(sph_handle *h, uint64_t n)
     h->have_step = false;
     h->n_ghost = 0;
     h->ghost_n[0] = h->ghost_n[1] = h->halo_n[0] = h->halo_n[1] = 0;
+    h->have_bbox_from_integration = false;
     return compute_bbox(h);
 }
 
@@ -1078,9 +1081,16 @@ int sph_slab_step_density(sph_handle *h)
     if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
     if (!h->slab_mode) return fail(h, SPH_ERR_STATE, "call sph_slab_enable(h, 1) first");
     if (h->n == 0) return SPH_OK;
-    rc = compute_bbox(h);  // arrivals and new ghosts are not covered by the integration's box
-    if (rc) return rc;
+    if (h->slab_fast && h->have_bbox_from_integration) {
+        // Sync-free paths: keep the box the last integration produced for the owned rows and widen it
+        // by one cell for the ghost layers and arrivals (anything further out is clamped, which is safe).
+        h->bbox_expand = 1;
+    } else {
+        rc = compute_bbox(h);  // arrivals and new ghosts are not covered by the integration's box
+        if (rc) return rc;
+    }
     rc = build_grid(h);
+    h->bbox_expand = 0;
     if (rc) return rc;
     const uint32_t n = (uint32_t)h->n;
     if (n) {
@@ -1133,6 +1143,8 @@ int sph_slab_step_forces(sph_handle *h, float dt)
         cudaStream_t s = h->stream;
         rc = launch_forces_integrate(h, n, dt);
         if (rc) return rc;
+        h->parity ^= 1;  // the integration accumulated the next step's box into the other slot
+        h->have_bbox_from_integration = true;
     }
     h->launches += 1;
     ++h->steps;

@@ -101,12 +101,14 @@ __global__ void k_reset_bbox(StepCounters *ctr, int parity)
 // side; if the box exceeds the dense-grid allocation the high side of the longest axis is clipped
 // (y first: it is the only unbounded axis) and grid_index() clamps the outliers into the last
 // interior layer.
-__device__ __forceinline__ GridDesc plan_grid(const int *b, uint32_t max_cells)
+__device__ __forceinline__ GridDesc plan_grid(const int *b, uint32_t max_cells, int expand)
 {
-    long long lo[3] = {b[0], b[1], b[2]};
+    // expand: extra cells on every side, for rows the box was not computed from (slab mode: the
+    // box comes from the owned rows' integration; ghosts and arrivals sit at most one cell outside).
+    long long lo[3] = {(long long)b[0] - expand, (long long)b[1] - expand, (long long)b[2] - expand};
     long long dim[3];
     for (int a = 0; a < 3; ++a) {
-        long long ext = (long long)b[3 + a] - lo[a] + 1;  // occupied cells on this axis
+        long long ext = (long long)b[3 + a] + expand - lo[a] + 1;  // occupied cells on this axis
         if (ext < 1) ext = 1;                              // empty box (n == 0)
         dim[a] = ext + 2;
     }
@@ -134,10 +136,10 @@ __device__ __forceinline__ GridDesc plan_grid(const int *b, uint32_t max_cells)
 // counts[0 .. ncells] (the extra entry becomes the end sentinel after the scan); block 0 publishes
 // the plan, re-arms bbox[parity^1] for this step's integration and resets the step counters.
 __global__ void __launch_bounds__(GRID_THREADS)
-k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, uint32_t *__restrict__ counts)
+k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, int expand, uint32_t *__restrict__ counts)
 {
     __shared__ GridDesc s_g;
-    if (threadIdx.x == 0) s_g = plan_grid(ctr->bbox[parity], max_cells);
+    if (threadIdx.x == 0) s_g = plan_grid(ctr->bbox[parity], max_cells, expand);
     __syncthreads();
     const uint32_t n = s_g.ncells + 1;
     const uint32_t n4 = n >> 2;

@@ -541,7 +541,7 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
                     driver.rebalance()
                 driver.step(s.dt)
                 if transport == "p2p" and not getattr(driver, "p2p_ready", False):
-                    driver.setup_p2p(2 * driver.suggest_halo_rows())
+                    driver.setup_p2p(driver.suggest_halo_rows(slack=2.0))
                 elif transport == "nccl":
                     driver.setup_fast(driver.suggest_halo_rows())
             elif transport == "p2p":
