@@ -148,6 +148,11 @@ uint64_t sph_capacity(const sph_handle *h);
 int sph_step(sph_handle *h, float dt, int nsteps);
 int sph_sync(sph_handle *h);
 
+/* Neighbour search alone, `repeats` times: hash cells, counting-sort the rows by cell, cell start
+ * offsets (replaces parallelCalculateHashes + sortParticles + createNeighborTable,
+ * src/sph.cpp:211-231). For the neighbour-search-only microbenchmark of BASELINE.json. */
+int sph_neighbor_search(sph_handle *h, int repeats);
+
 /* Stateless form with the exact data contract of updateParticlesGPU
  * (src/kernels/sphGPU.h:8-11): `host_particles` is an array of n 60-byte reference Particle
  * records (src/Particle.h:4-10: position, velocity, acceleration, force, density, pressure,
@@ -255,6 +260,10 @@ int sph_slab_pack_halo_density(sph_handle *h, int side, void *dev_buf);
 int sph_slab_set_ghost_density(sph_handle *h, int side, const void *dev_buf, uint64_t nrows);
 /* Forces + integration of the owned rows. */
 int sph_slab_step_forces(sph_handle *h, float dt);
+/* Read back the owned rows only (ghost and dropped rows skipped), compacted, in arbitrary order,
+ * with their ids; host buffers hold capacity_rows rows. */
+int sph_slab_download_owned(sph_handle *h, float *host_pos_xyz, float *host_vel_xyz, uint32_t *host_id,
+                            uint64_t capacity_rows, uint64_t *count_out);
 /* Histogram of cell.x over owned rows, bins [x_cell_lo, x_cell_lo + nbins), ends clamped. */
 int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, uint64_t *host_hist);
 

@@ -88,6 +88,7 @@ def load_library() -> C.CDLL:
         "sph_capacity": ([hp], C.c_uint64),
         "sph_step": ([hp, C.c_float, C.c_int], C.c_int),
         "sph_sync": ([hp], C.c_int),
+        "sph_neighbor_search": ([hp, C.c_int], C.c_int),
         "sph_update_particles_aos": ([hp, C.c_void_p, fp, C.c_uint64, C.c_float], C.c_int),
         "sph_hash_table": ([hp, u32p], C.c_int),
         "sph_neighbor_lists": ([hp, u32p, u64p, u32p, C.c_uint64, u32p], C.c_int),
@@ -109,6 +110,7 @@ def load_library() -> C.CDLL:
         "sph_slab_pack_halo_density": ([hp, C.c_int, C.c_void_p], C.c_int),
         "sph_slab_set_ghost_density": ([hp, C.c_int, C.c_void_p, C.c_uint64], C.c_int),
         "sph_slab_step_forces": ([hp, C.c_float], C.c_int),
+        "sph_slab_download_owned": ([hp, fp, fp, u32p, C.c_uint64, u64p], C.c_int),
         "sph_slab_xcell_histogram": ([hp, C.c_int32, C.c_uint32, u64p], C.c_int),
         "sph_scene_block_slice": ([C.c_int] * 3 + [C.c_float] * 5 + [C.c_uint, C.c_int, C.c_int, fp, fp, u32p], C.c_int),
         "sph_slab_fast_begin": ([hp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p], C.c_int),
@@ -295,6 +297,9 @@ class Sim:
 
     def sync(self):
         self._ck(self.lib.sph_sync(self._h))
+
+    def neighbor_search(self, repeats=1):
+        self._ck(self.lib.sph_neighbor_search(self._h, repeats))
 
     def update_particles_aos(self, particles: np.ndarray, dt=0.0, transforms=True):
         """particles: (n, 15) uint32 view of reference Particle rows (60 bytes each), in place."""

@@ -731,6 +731,24 @@ int sph_step(sph_handle *h, float dt, int nsteps)
     return SPH_OK;
 }
 
+// Neighbour search only (cell hash, counting sort by cell, cell start offsets) for the current
+// positions: BASELINE.json config 4. Rows end up cell-sorted; no physics is run.
+int sph_neighbor_search(sph_handle *h, int repeats)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (h->n == 0) return SPH_OK;
+    for (int k = 0; k < repeats; ++k) {
+        // the box of the current positions is in bbox[parity]; the plan re-arms the other slot only
+        rc = build_grid(h);
+        if (rc) return rc;
+        h->launches += 5;
+    }
+    h->have_step = false;
+    return SPH_OK;
+}
+
 int sph_sync(sph_handle *h)
 {
     int rc = enter_exact(h);
@@ -1149,6 +1167,42 @@ int sph_slab_step_forces(sph_handle *h, float dt)
     h->launches += 1;
     ++h->steps;
     h->have_step = true;
+    return SPH_OK;
+}
+
+int sph_slab_download_owned(sph_handle *h, float *host_pos_xyz, float *host_vel_xyz, uint32_t *host_id,
+                            uint64_t capacity_rows, uint64_t *count_out)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!host_pos_xyz || !host_vel_xyz || !host_id || !count_out) return fail(h, SPH_ERR_INVALID, "NULL argument");
+    const uint64_t n = h->n;
+    const uint64_t cap = capacity_rows < n ? capacity_rows : n;
+    const size_t b3 = align_up(sizeof(float) * 3 * (cap ? cap : 1), 256), b1 = align_up(sizeof(uint32_t) * (cap ? cap : 1), 256);
+    rc = ensure_scratch(h, 2 * b3 + b1 + 256);
+    if (rc) return rc;
+    char *sc = (char *)h->scratch;
+    unsigned long long *cursor = h->slab_counts + 2 * SLAB_MAX_RANKS + 6;
+    CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), h->stream));
+    if (n) {
+        k_slab_export_owned<<<blocks_for(n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
+            h->pos[h->cur], h->vel[h->cur], (uint32_t)n, (uint32_t)cap, cursor, (float *)sc, (float *)(sc + b3),
+            (uint32_t *)(sc + 2 * b3));
+        CK_LAUNCH();
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, cursor, sizeof cnt, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (cnt > capacity_rows)
+        return fail(h, SPH_ERR_CAPACITY, "%llu owned rows, buffers hold %llu", cnt, (unsigned long long)capacity_rows);
+    if (cnt) {
+        CK(cudaMemcpyAsync(host_pos_xyz, sc, sizeof(float) * 3 * cnt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(host_vel_xyz, sc + b3, sizeof(float) * 3 * cnt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(host_id, sc + 2 * b3, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    *count_out = cnt;
     return SPH_OK;
 }
 

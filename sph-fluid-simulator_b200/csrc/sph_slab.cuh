@@ -241,6 +241,25 @@ k_slab_set_ghost_density(float4 *__restrict__ vel, const uint32_t *__restrict__ 
     if (k < nrows) vel[inverse[first + k]].w = in[k];
 }
 
+// Compact the live owned rows into xyz / xyz / id columns (order arbitrary), for host read-back.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_slab_export_owned(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, uint32_t cap,
+                    unsigned long long *__restrict__ cursor, float *__restrict__ pos3, float *__restrict__ vel3,
+                    uint32_t *__restrict__ ids)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    const uint32_t w = __float_as_uint(p.w);
+    if (w & W_GHOST) return;  // ghost or dropped row
+    const unsigned long long k = atomicAdd(cursor, 1ull);
+    if (k >= cap) return;
+    const float4 v = vel[i];
+    pos3[3 * k] = p.x; pos3[3 * k + 1] = p.y; pos3[3 * k + 2] = p.z;
+    vel3[3 * k] = v.x; vel3[3 * k + 1] = v.y; vel3[3 * k + 2] = v.z;
+    ids[k] = w;
+}
+
 // Histogram of cell.x over live owned rows, bins [x_lo, x_lo + nbins) with clamping at both ends
 // (used to choose balanced cuts).
 __global__ void __launch_bounds__(SLAB_THREADS)

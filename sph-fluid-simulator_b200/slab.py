@@ -582,6 +582,50 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     else:
         owned_list = [int(owned.item())]
     clk = clocks.stop()
+
+    # ---- end to end: every step uploads the rank's rows from pinned host memory, steps through the
+    # slab driver (general path: an upload resets the resident state) and reads positions and
+    # velocities back to the host.
+    e2e = None
+    if args.e2e_steps > 0:
+        cap_rows = int(sim.lib.sph_capacity(sim.handle))
+        hp = torch.empty((cap_rows, 3), dtype=torch.float32).pin_memory()
+        hv = torch.empty((cap_rows, 3), dtype=torch.float32).pin_memory()
+        hi = torch.empty(cap_rows, dtype=torch.int32).pin_memory()
+        fp, u32p = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+        pp, pv, pi_ = C.cast(hp.data_ptr(), fp), C.cast(hv.data_ptr(), fp), C.cast(hi.data_ptr(), u32p)
+        cnt = C.c_uint64(0)
+
+        def read_back():
+            rc = sim.lib.sph_slab_download_owned(sim.handle, pp, pv, pi_, cap_rows, C.byref(cnt))
+            if rc:
+                raise RuntimeError(sim.lib.sph_last_error(sim.handle).decode())
+            return int(cnt.value)
+
+        m = read_back()
+        k_e2e = max(2, min(args.e2e_steps, 5))
+        t_e2e = 0.0
+        import time
+        for k in range(k_e2e + 1):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            rc = sim.lib.sph_upload(sim.handle, m, pp, pv, pi_)   # pinned host rows -> device
+            if rc:
+                raise RuntimeError(sim.lib.sph_last_error(sim.handle).decode())
+            driver.step(s.dt)
+            m = read_back()                                       # owned rows -> pinned host
+            if world > 1:
+                dist.barrier()
+            if k > 0:  # first iteration is warm-up
+                t_e2e += time.perf_counter() - t0
+        tt = torch.tensor([t_e2e], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total * k_e2e / float(tt.item()), "unit": UNIT, "steps": k_e2e,
+               "h2d_bytes_per_step": 28 * n_total, "d2h_bytes_per_step": 28 * n_total,
+               "call": "per rank: sph_upload(pos, vel, id in pinned host memory) -> slab step (general path) -> "
+                       "sph_slab_download_owned(pos, vel, id into pinned host memory)"}
     if driver.profile:
         print(f"[rank {rank}] phase ms/step:", {k: round(1e3 * v / max(driver.stats['steps'], 1), 3) for k, v in driver.phase_s.items()},
               file=sys.stderr, flush=True)
@@ -607,7 +651,7 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
                        "migrated_rows_rank0": driver.stats["migrated_rows"], "halo_rows_rank0": driver.stats["halo_rows"],
                        "phase_ms_per_step_rank0": {k: 1e3 * v / max(driver.stats["steps"], 1) for k, v in driver.phase_s.items()}},
             "clocks": clk,
-            "e2e": None,
+            "e2e": e2e,
             "gpu_launches": int(sim.launch_count - launches0),
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": 292.0 * value / world / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": 292.0 * value / world / 1e9 / peak, "traffic": None,
