@@ -276,15 +276,16 @@ int build_grid(sph_handle *h)
 // Launch-shape variants of the density kernel (SPH_B200_DENSITY_CFG, experiments).
 int launch_density(sph_handle *h, uint32_t n)
 {
-#define LAUNCH_D(S, B)                                                                                     \
-    k_density<S, B><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(                             \
+#define LAUNCH_D(S, B, U)                                                                                  \
+    k_density<S, B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(                          \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap)
     switch (h->density_cfg) {
-    case 1: LAUNCH_D(16, 16); break;
-    case 2: LAUNCH_D(24, 12); break;
-    case 3: LAUNCH_D(16, 12); break;
-    case 4: LAUNCH_D(12, 16); break;
-    default: LAUNCH_D(24, 1); break;
+    case 1: LAUNCH_D(24, 1, 4); break;
+    case 2: LAUNCH_D(24, 1, 2); break;
+    case 3: LAUNCH_D(24, 12, 4); break;
+    case 4: LAUNCH_D(24, 1, 3); break;
+    case 5: LAUNCH_D(24, 1, 1); break;
+    default: LAUNCH_D(24, 12, 2); break;  // 40 registers: best of the shapes tried at both 1 M (dense) and 8 M (sparse)
     }
 #undef LAUNCH_D
     CK_LAUNCH();

@@ -31,13 +31,14 @@ __device__ __forceinline__ void bbox_accumulate(int *bb, int cx, int cy, int cz,
     mxy = __reduce_max_sync(0xffffffffu, mxy);
     mxz = __reduce_max_sync(0xffffffffu, mxz);
     if ((threadIdx.x & 31) == 0) {
-        // Plain reads first: the box is monotone, so a stale value only costs a redundant atomic.
-        if (mnx < bb[0]) atomicMin(&bb[0], mnx);
-        if (mny < bb[1]) atomicMin(&bb[1], mny);
-        if (mnz < bb[2]) atomicMin(&bb[2], mnz);
-        if (mxx > bb[3]) atomicMax(&bb[3], mxx);
-        if (mxy > bb[4]) atomicMax(&bb[4], mxy);
-        if (mxz > bb[5]) atomicMax(&bb[5], mxz);
+        // Read first (ld.cg: past the L1, which could hold a stale line for the whole kernel): the box
+        // is monotone, so after the first few warps almost no atomic is issued.
+        if (mnx < __ldcg(&bb[0])) atomicMin(&bb[0], mnx);
+        if (mny < __ldcg(&bb[1])) atomicMin(&bb[1], mny);
+        if (mnz < __ldcg(&bb[2])) atomicMin(&bb[2], mnz);
+        if (mxx > __ldcg(&bb[3])) atomicMax(&bb[3], mxx);
+        if (mxy > __ldcg(&bb[4])) atomicMax(&bb[4], mxy);
+        if (mxz > __ldcg(&bb[5])) atomicMax(&bb[5], mxz);
     }
 }
 
@@ -71,6 +72,53 @@ __device__ __forceinline__ void bbox_accumulate_block(int *bb, int cx, int cy, i
             if (v[lane] < __ldcg(&bb[lane])) atomicMin(&bb[lane], v[lane]);
         } else if (lane < 6) {
             if (v[lane] > __ldcg(&bb[lane])) atomicMax(&bb[lane], v[lane]);
+        }
+    }
+}
+
+// Barrier-free block-level variant for kernels whose warps finish at very different times: every
+// warp folds its reduction into shared memory with atomics and retires; the last warp of the block
+// to arrive (shared counter) carries the block's box to global memory. The caller initialises
+// s_box / s_done at kernel entry (BboxShared::init, one early barrier while all warps are in step).
+struct BboxShared {
+    int box[6];
+    unsigned int done;
+    __device__ __forceinline__ void init()
+    {
+        if (threadIdx.x < 3) box[threadIdx.x] = 0x7fffffff;
+        else if (threadIdx.x < 6) box[threadIdx.x] = -0x7fffffff - 1;
+        if (threadIdx.x == 6) done = 0;
+        __syncthreads();
+    }
+};
+
+__device__ __forceinline__ void bbox_accumulate_late(int *bb, BboxShared &sh, int cx, int cy, int cz, bool valid)
+{
+    const int big = 0x7fffffff;
+    int v[6] = {valid ? cx : big, valid ? cy : big, valid ? cz : big,
+                valid ? cx : -big - 1, valid ? cy : -big - 1, valid ? cz : -big - 1};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v[k] = __reduce_min_sync(0xffffffffu, v[k]);
+#pragma unroll
+    for (int k = 3; k < 6; ++k) v[k] = __reduce_max_sync(0xffffffffu, v[k]);
+    const int lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+    if (lane < 3) atomicMin(&sh.box[lane], v[lane]);
+    else if (lane < 6) atomicMax(&sh.box[lane], v[lane]);
+    __syncwarp();
+    unsigned int last = 0;
+    if (lane == 0) {
+        __threadfence_block();
+        last = atomicAdd(&sh.done, 1u) == (unsigned)(nwarps - 1);
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        __threadfence_block();
+        if (lane < 3) {
+            const int b = sh.box[lane];
+            if (b < __ldcg(&bb[lane])) atomicMin(&bb[lane], b);
+        } else if (lane < 6) {
+            const int b = sh.box[lane];
+            if (b > __ldcg(&bb[lane])) atomicMax(&bb[lane], b);
         }
     }
 }
@@ -185,7 +233,7 @@ k_cell_hist(const float4 *__restrict__ pos, uint32_t n, float h, const GridDesc 
 // ---- single-pass exclusive scan (decoupled look-back) ---------------------------------------
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_ITEMS = 16;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 constexpr uint32_t SCAN_AGG = 1, SCAN_INCL = 2;
 
@@ -216,10 +264,11 @@ k_scan_exclusive(uint32_t *__restrict__ data, const uint32_t *__restrict__ n_ptr
         const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
         uint32_t v[SCAN_ITEMS];
         if (base + SCAN_ITEMS <= n) {
-            const uint4 a = *reinterpret_cast<const uint4 *>(data + base);
-            const uint4 b = *reinterpret_cast<const uint4 *>(data + base + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+                const uint4 a = *reinterpret_cast<const uint4 *>(data + base + 4 * q);
+                v[4 * q] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < n) ? data[base + k] : 0u;
@@ -268,8 +317,9 @@ k_scan_exclusive(uint32_t *__restrict__ data, const uint32_t *__restrict__ n_ptr
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; ++k) { o[k] = run; run += v[k]; }
         if (base + SCAN_ITEMS <= n) {
-            *reinterpret_cast<uint4 *>(data + base) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4 *>(data + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q)
+                *reinterpret_cast<uint4 *>(data + base + 4 * q) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         } else {
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k)

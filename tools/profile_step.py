@@ -26,7 +26,9 @@ sim = S.Sim(s, capacity=pos.shape[0])
 sim.upload(pos, vel)
 sim.step(args.settle)
 sim.sync()
+sim.enable_pass_timing(True)
 sim.step(args.steps)
 sim.sync()
+print("pass ms/step", sim.pass_times())
 st = sim.stats()
 print("particles", pos.shape[0], "mean density", st.mean_density, "grid", list(st.grid_dim), "nan", st.nan_count)
