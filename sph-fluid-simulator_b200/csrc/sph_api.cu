@@ -81,7 +81,9 @@ struct sph_handle {
     uint32_t epoch = 0;
     int parity = 0;
     bool have_state = false;  // particles uploaded
-    bool have_step = false;   // force / density / hash16 rows are valid and aligned with pos / vel
+    bool have_step = false;   // density / hash16 rows are valid and aligned with pos / vel
+    bool have_force = false;  // the force column holds the last step's forces
+    bool write_force = false; // the next step writes the force column (drop-in call)
 
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -292,26 +294,49 @@ int launch_density(sph_handle *h, uint32_t n)
     return SPH_OK;
 }
 
-// Launch-shape variants of the fused forces+integration kernel (SPH_B200_FORCES_CFG, experiments).
-int launch_forces_integrate(sph_handle *h, uint32_t n, float dt)
+// Launch of the fused forces+integration kernel. mode: FI_STEP (resident simulation: no force
+// column), FI_STEP_WRITE_FORCE (the stateless drop-in call fills Particle::force every step) or
+// FI_FORCE_ONLY (recompute the force column of the last step on demand; start-of-step rows are in
+// the other buffers). SPH_B200_FORCES_CFG selects launch shapes for experiments.
+int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
 {
     cudaStream_t s = h->stream;
-#define LAUNCH_FI(T, B)                                                                                          \
-    k_forces_integrate<T, B><<<blocks_for(n, T), T, 0, s>>>(                                                      \
-        h->pos[h->cur], h->vel[h->cur], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap,          \
-        dt, h->pos[h->cur ^ 1], h->vel[h->cur ^ 1], h->force, h->ctr, h->parity ^ 1)
-    switch (h->forces_cfg) {
-    case 1: LAUNCH_FI(128, 8); break;
-    case 2: LAUNCH_FI(128, 10); break;
-    case 3: LAUNCH_FI(64, 16); break;
-    case 4: LAUNCH_FI(256, 4); break;
-    case 5: LAUNCH_FI(128, 12); break;
-    default: LAUNCH_FI(128, 1); break;
+    // FI_FORCE_ONLY reads the start-of-step rows, which after the step live in the non-current buffers
+    const int in = mode == FI_FORCE_ONLY ? (h->cur ^ 1) : h->cur;
+#define LAUNCH_FI(T, B, M)                                                                                       \
+    k_forces_integrate<T, B, M><<<blocks_for(n, T), T, 0, s>>>(                                                   \
+        h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt,              \
+        h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1)
+    if (mode == FI_FORCE_ONLY) {
+        LAUNCH_FI(128, 10, FI_FORCE_ONLY);
+    } else if (mode == FI_STEP_WRITE_FORCE) {
+        LAUNCH_FI(128, 10, FI_STEP_WRITE_FORCE);
+    } else {
+        switch (h->forces_cfg) {
+        case 1: LAUNCH_FI(128, 8, FI_STEP); break;
+        case 3: LAUNCH_FI(64, 16, FI_STEP); break;
+        case 4: LAUNCH_FI(256, 4, FI_STEP); break;
+        case 5: LAUNCH_FI(128, 12, FI_STEP); break;
+        default: LAUNCH_FI(128, 10, FI_STEP); break;
+        }
     }
 #undef LAUNCH_FI
     CK_LAUNCH();
-    h->cur ^= 1;
+    if (mode != FI_FORCE_ONLY) {
+        h->cur ^= 1;
+        h->have_force = mode == FI_STEP_WRITE_FORCE;
+    } else {
+        h->have_force = true;
+    }
     return SPH_OK;
+}
+
+// Make sure the force column of the last step exists (it is not written by a plain step).
+int ensure_force(sph_handle *h)
+{
+    if (h->have_force) return SPH_OK;
+    if (!h->have_step) return fail(h, SPH_ERR_STATE, "forces are only defined after a step");
+    return launch_forces_integrate(h, (uint32_t)h->n, 0.f, FI_FORCE_ONLY);
 }
 
 int step_once(sph_handle *h, float dt)
@@ -335,7 +360,7 @@ int step_once(sph_handle *h, float dt)
     rc = launch_density(h, n);
     if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[2], s));
-    rc = launch_forces_integrate(h, n, dt);
+    rc = launch_forces_integrate(h, n, dt, h->write_force ? FI_STEP_WRITE_FORCE : FI_STEP);
     if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[3], s));
     if (timed) CK(cudaEventRecord(ev[4], s));
@@ -616,6 +641,10 @@ int sph_download(sph_handle *h, int order, float *host_pos, float *host_vel, flo
         return fail(h, SPH_ERR_INVALID, "unknown order %d", order);
     const uint64_t n = h->n;
     if (n == 0) return SPH_OK;
+    if (host_force) {
+        rc = ensure_force(h);
+        if (rc) return rc;
+    }
     const size_t b3 = align_up(sizeof(float) * 3 * n, 256), b1 = align_up(sizeof(float) * n, 256);
     rc = ensure_scratch(h, 3 * b3 + 4 * b1 + 256);
     if (rc) return rc;
@@ -779,7 +808,9 @@ int sph_update_particles_aos(sph_handle *h, void *host_particles, float *host_ma
     CK_LAUNCH();
     rc = after_upload(h, n);
     if (rc) return rc;
+    h->write_force = true;  // Particle::force is part of this call's output
     rc = step_once(h, dt);
+    h->write_force = false;
     if (rc) return rc;
     rc = build_hash16_order(h, true);
     if (rc) return rc;
@@ -1160,7 +1191,7 @@ int sph_slab_step_forces(sph_handle *h, float dt)
     const uint32_t n = (uint32_t)h->n;
     if (n) {
         cudaStream_t s = h->stream;
-        rc = launch_forces_integrate(h, n, dt);
+        rc = launch_forces_integrate(h, n, dt, FI_STEP);
         if (rc) return rc;
         h->parity ^= 1;  // the integration accumulated the next step's box into the other slot
         h->have_bbox_from_integration = true;
