@@ -12,7 +12,7 @@ col = {n: i for i, n in enumerate(hdr)}
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 acc = collections.defaultdict(list)
 for r in data:
-    name = r[col["Kernel Name"]].split("(")[0].split("<")[0].replace("sphb::", "")
+    name = r[col["Kernel Name"]].split("(")[0].split("<")[0].replace("sphb::", "").replace("void ", "").strip()
     tot = 0.0
     for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         tot += float(r[col[k]].replace(",", "")) * scale[units[col[k]]]
