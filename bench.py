@@ -277,6 +277,17 @@ def run_single_gpu(args):
                "sample": f"{cs} steps of the full {n}-particle settled state (after {args.settle} GPU steps), "
                          f"{sec:.1f} s of wall time"}
 
+    # ---- secondary baseline: the reference's own CUDA path on this GPU (subprocess, bounded) ----
+    ref_cuda = None
+    if not args.no_cpu_baseline:
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_reference_cuda.py")],
+                                 capture_output=True, text=True, timeout=180)
+            rows = [l for l in out.stdout.splitlines() if l.startswith("{")]
+            ref_cuda = json.loads(rows[-1]) if rows else {"unavailable": (out.stderr or "no output")[-200:]}
+        except Exception as e:  # noqa: BLE001 - a crash of that code must not take the bench down
+            ref_cuda = {"unavailable": repr(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -293,6 +304,7 @@ def run_single_gpu(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "reference_cuda_baseline": ref_cuda,
     }
     print(json.dumps(line), flush=True)
     sim.close()

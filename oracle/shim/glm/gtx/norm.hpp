@@ -3,5 +3,5 @@
 #include "../glm.hpp"
 
 namespace glm {
-inline float length2(const vec3 &v) { return dot(v, v); }
+GLM_SHIM_HD inline float length2(const vec3 &v) { return dot(v, v); }
 } // namespace glm

@@ -5,12 +5,12 @@
 #include "../glm.hpp"
 
 namespace glm {
-inline mat4 translate(const vec3 &v) {
+GLM_SHIM_HD inline mat4 translate(const vec3 &v) {
     mat4 m(1.0f);
     m[3] = m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3];
     return m;
 }
-inline mat4 scale(const vec3 &s) {
+GLM_SHIM_HD inline mat4 scale(const vec3 &s) {
     mat4 m(1.0f), r;
     r[0] = m[0] * s.x; r[1] = m[1] * s.y; r[2] = m[2] * s.z; r[3] = m[3];
     return r;
