@@ -280,7 +280,8 @@ int launch_density(sph_handle *h, uint32_t n)
 {
 #define LAUNCH_D(S, B, U)                                                                                  \
     k_density<S, B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(                          \
-        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap)
+        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
+        h->order, h->ctr)
     switch (h->density_cfg) {
     case 1: LAUNCH_D(24, 1, 4); break;
     case 2: LAUNCH_D(24, 1, 2); break;
@@ -290,6 +291,10 @@ int launch_density(sph_handle *h, uint32_t n)
     default: LAUNCH_D(24, 12, 2); break;  // 40 registers: best of the shapes tried at both 1 M (dense) and 8 M (sparse)
     }
 #undef LAUNCH_D
+    CK_LAUNCH();
+    // the heavy tail (clumps, hash-collision cells), one warp per deferred particle; exits at once when empty
+    k_density_heavy<<<h->num_sms * 4, HEAVY_THREADS, 0, h->stream>>>(h->pos[h->cur], h->gd, h->cells, h->P, h->vel[h->cur],
+                                                                    h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
     CK_LAUNCH();
     return SPH_OK;
 }
@@ -306,8 +311,13 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
 #define LAUNCH_FI(T, B, M)                                                                                       \
     k_forces_integrate<T, B, M><<<blocks_for(n, T), T, 0, s>>>(                                                   \
         h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt,              \
-        h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1)
+        h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map)
+#define LAUNCH_FH(M)                                                                                              \
+    k_forces_heavy<M><<<h->num_sms * 4, HEAVY_THREADS, 0, s>>>(h->pos[in], h->vel[in], h->gd, h->cells, h->P, dt,  \
+                                                              h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr,   \
+                                                              h->parity ^ 1, h->map)
     if (mode == FI_FORCE_ONLY) {
+        CK(cudaMemsetAsync(&h->ctr->heavy[1], 0, sizeof(uint32_t), s));  // the step's deferral list is rebuilt
         LAUNCH_FI(128, 10, FI_FORCE_ONLY);
     } else if (mode == FI_STEP_WRITE_FORCE) {
         LAUNCH_FI(128, 10, FI_STEP_WRITE_FORCE);
@@ -321,6 +331,11 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
         }
     }
 #undef LAUNCH_FI
+    CK_LAUNCH();
+    if (mode == FI_FORCE_ONLY) LAUNCH_FH(FI_FORCE_ONLY);
+    else if (mode == FI_STEP_WRITE_FORCE) LAUNCH_FH(FI_STEP_WRITE_FORCE);
+    else LAUNCH_FH(FI_STEP);
+#undef LAUNCH_FH
     CK_LAUNCH();
     if (mode != FI_FORCE_ONLY) {
         h->cur ^= 1;
@@ -364,7 +379,7 @@ int step_once(sph_handle *h, float dt)
     if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[3], s));
     if (timed) CK(cudaEventRecord(ev[4], s));
-    h->launches += 7;  // plan+zero, hist, scan, place, order+gather, density, forces+integrate
+    h->launches += 9;  // plan+zero, hist, scan, place, order+gather, density (+heavy), forces+integrate (+heavy)
     h->parity ^= 1;
     ++h->steps;
     h->have_step = true;
@@ -1147,7 +1162,7 @@ int sph_slab_step_density(sph_handle *h)
         rc = launch_density(h, n);
         if (rc) return rc;
     }
-    h->launches += 6;
+    h->launches += 7;
     return SPH_OK;
 }
 
@@ -1196,7 +1211,7 @@ int sph_slab_step_forces(sph_handle *h, float dt)
         h->parity ^= 1;  // the integration accumulated the next step's box into the other slot
         h->have_bbox_from_integration = true;
     }
-    h->launches += 1;
+    h->launches += 2;
     ++h->steps;
     h->have_step = true;
     return SPH_OK;

@@ -49,6 +49,7 @@ struct StepCounters {
     uint32_t ticket;      // tile ticket of the scan
     uint32_t clamped;     // particles clamped into the grid this step
     uint32_t aux[4];
+    uint32_t heavy[2];    // particles deferred to the warp-cooperative density / force kernels
 };
 
 // Settings + derived constants, passed to kernels by value.

@@ -200,6 +200,7 @@ k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, int
             *gd = s_g;
             ctr->ticket = 0;
             ctr->clamped = 0;
+            ctr->heavy[0] = ctr->heavy[1] = 0;
             int *nb = ctr->bbox[parity ^ 1];
             nb[0] = nb[1] = nb[2] = 0x7fffffff;
             nb[3] = nb[4] = nb[5] = -0x7fffffff - 1;
