@@ -946,6 +946,9 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     out->grid_dim[0] = g.nx; out->grid_dim[1] = g.ny; out->grid_dim[2] = g.nz;
     out->grid_cells = g.ncells;
     out->clamped = c.clamped;
+    out->deferred_density = c.heavy[0];
+    out->deferred_forces = c.heavy[1];
+    out->nlist_rows = NLIST_ROWS;
     out->nan_count = a.nan_count;
     if (h->have_step) out->count = a.owned;
     out->mean_density = a.sum_rho / (double)(a.owned ? a.owned : 1);

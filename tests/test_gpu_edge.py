@@ -113,6 +113,42 @@ np.savez(sys.argv[1], clamped=st.clamped, cells=st.grid_cells, **out)
     assert_fields_close(clipped, full, "clipped grid")
 
 
+def test_clump_takes_the_warp_cooperative_kernels(sph, oracle):
+    """A clump (hundreds of neighbours per particle, what the reference's fluid collapses into after
+    ~2000 steps) overflows the per-particle neighbour list and the per-run budget of the one-thread
+    kernels: those particles are deferred to kernels that put a warp on each. Same neighbour
+    multisets, same tolerances, and the same bits every time."""
+    rng = np.random.default_rng(5)
+    s = sph.default_settings()
+    d = rng.normal(size=(1500, 3))
+    d *= (0.25 * rng.uniform(0, 1, (1500, 1)) ** (1 / 3)) / np.linalg.norm(d, axis=1, keepdims=True)
+    pos = np.concatenate([d + [1.0, 1.0, 1.0], rng.uniform([-3, 0.2, -3], [3, 3, 3], (2500, 3))]).astype(np.float32)
+    vel = rng.normal(0, 0.5, pos.shape).astype(np.float32)
+    os_ = oracle.settings(s.as_tuple7())
+    want = by_id(oracle.step(os_, s.dt, pos, vel))
+    runs = []
+    for _ in range(2):
+        sim = sph.Sim(s, capacity=len(pos))
+        sim.upload(pos, vel)
+        ids, counts, offs, lst = sim.neighbor_lists()
+        sim.step(1)
+        st = sim.stats()
+        runs.append((sim.download(sph.ORDER_ID), counts[np.argsort(ids)]))
+        sim.close()
+    got, counts = runs[0]
+    assert st.deferred_density >= 1400 and st.deferred_forces >= 1400 and st.nlist_rows < counts.max()
+    order, ocounts, _, _, _ = oracle.neighbor_lists(os_, pos)
+    assert np.array_equal(counts, ocounts[np.argsort(order)]) and counts.max() > 300
+    assert np.array_equal(got["hash"], want["hash"])
+    rel = np.abs(got["density"] - want["density"]) / want["density"]
+    assert rel.max() <= 1e-5, f"density rel err {rel.max():.3e}"
+    fn = np.linalg.norm(want["force"], axis=1)
+    fe = np.linalg.norm(got["force"] - want["force"], axis=1) / np.maximum(fn, np.median(fn[:1500]))
+    assert fe.max() <= 1e-3, f"force rel err {fe.max():.3e}"
+    for k in ("pos", "vel", "force", "density"):
+        assert_bit_equal(runs[1][0][k], got[k], f"second run: {k}")
+
+
 def test_errors_are_reported_not_thrown(sph):
     s = sph.default_settings()
     sim = sph.Sim(s, capacity=10)

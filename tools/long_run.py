@@ -20,4 +20,4 @@ for w in range(nwin):
     pt = sim.pass_times(); sim.enable_pass_timing(False)
     st = sim.stats()
     print(f"steps {(w+1)*win:6d}  ms/step {e0.elapsed_time(e1)/win:.4f}  grid {pt['grid']:.3f} dens {pt['density']:.3f} forces {pt['forces']:.3f}  "
-          f"mean rho {st.mean_density:.2f} max rho {st.max_density:.0f} KE {st.kinetic_energy:.1f} nan {st.nan_count} grid {list(st.grid_dim)}", flush=True)
+          f"mean rho {st.mean_density:.2f} max rho {st.max_density:.0f} KE {st.kinetic_energy:.1f} nan {st.nan_count} grid {list(st.grid_dim)} deferred d/f {st.deferred_density}/{st.deferred_forces} rows {st.nlist_rows}", flush=True)
