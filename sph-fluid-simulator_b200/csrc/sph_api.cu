@@ -78,7 +78,6 @@ struct sph_handle {
     GridDesc *gd = nullptr;
     StepCounters *ctr = nullptr;
     StatsAccum *stats_acc = nullptr;
-    uint32_t epoch = 0;
     int parity = 0;
     bool have_state = false;  // particles uploaded
     bool have_step = false;   // density / hash16 rows are valid and aligned with pos / vel
@@ -95,6 +94,21 @@ struct sph_handle {
     size_t ev_used = 0;
     static constexpr size_t kMaxTimedSteps = 16384;
     uint64_t launches = 0;  // kernels launched by sph_step / sph_update_particles_aos so far
+
+    // Captured steps. A resident step takes no decision on the host (the grid plan, the row counts and
+    // the scan epoch all live on the device), so sph_step replays CUDA graphs of 1 and kGraphLong
+    // steps, one per bounding-box parity at entry, captured on first use for the current key.
+    static constexpr int kGraphLong = 16;
+    struct GraphKey {
+        uint64_t n;
+        float dt;
+        int cur, write_force, bbox_expand, forces_cfg, density_cfg;
+        uint32_t max_cells;
+        Params P;
+    };
+    GraphKey graph_key;
+    cudaGraphExec_t graphs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [1 | kGraphLong steps][parity]
+    bool graph_enabled = true;  // SPH_B200_GRAPH=0 launches every kernel from the host
 
     char err[512] = "";
 };
@@ -241,9 +255,8 @@ int build_grid(sph_handle *h)
     k_cell_hist<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->pos[h->cur], n, h->P.h, h->gd, h->cells,
                                                                    h->cell_rank, h->ctr);
     CK_LAUNCH();
-    ++h->epoch;
     k_scan_exclusive<<<h->num_sms * 4, SCAN_THREADS, 0, s>>>(h->cells, &h->gd->ncells, h->tile_state,
-                                                            &h->ctr->ticket, h->epoch);
+                                                            &h->ctr->ticket, &h->ctr->epoch);
     CK_LAUNCH();
     k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot);
     CK_LAUNCH();
@@ -386,6 +399,68 @@ int step_once(sph_handle *h, float dt)
     return SPH_OK;
 }
 
+void drop_graphs(sph_handle *h)
+{
+    for (auto &row : h->graphs)
+        for (auto &g : row)
+            if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
+
+// Captures `len` steps from the current host state into an executable graph. Nothing runs, so the
+// bookkeeping step_once did on the host is rolled back.
+int capture_steps(sph_handle *h, float dt, int len, cudaGraphExec_t *out)
+{
+    const int cur = h->cur, parity = h->parity;
+    const uint64_t steps = h->steps, launches = h->launches;
+    const bool have_step = h->have_step, have_force = h->have_force;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = SPH_OK;
+    for (int k = 0; k < len && !rc; ++k) rc = step_once(h, dt);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->cur = cur; h->parity = parity; h->steps = steps; h->launches = launches;
+    h->have_step = have_step; h->have_force = have_force;
+    if (rc) {
+        if (g) cudaGraphDestroy(g);
+        return rc;
+    }
+    CK(e);
+    const cudaError_t ei = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    CK(ei);
+    return SPH_OK;
+}
+
+// nsteps resident steps through the captured graphs.
+int step_graphs(sph_handle *h, float dt, int nsteps)
+{
+    sph_handle::GraphKey key;
+    std::memset(&key, 0, sizeof key);
+    key.n = h->n; key.dt = dt; key.cur = h->cur; key.write_force = h->write_force; key.bbox_expand = h->bbox_expand;
+    key.forces_cfg = h->forces_cfg; key.density_cfg = h->density_cfg; key.max_cells = h->max_cells; key.P = h->P;
+    if (std::memcmp(&key, &h->graph_key, sizeof key)) {
+        drop_graphs(h);
+        h->graph_key = key;
+    }
+    for (int k = 0; k < nsteps;) {
+        const int li = nsteps - k >= sph_handle::kGraphLong ? 1 : 0;
+        const int len = li ? sph_handle::kGraphLong : 1;
+        cudaGraphExec_t &ex = h->graphs[li][h->parity];
+        if (!ex) {
+            int rc = capture_steps(h, dt, len, &ex);
+            if (rc) return rc;
+        }
+        CK(cudaGraphLaunch(ex, h->stream));
+        h->steps += len;
+        h->launches += 9ull * len;
+        if (len & 1) h->parity ^= 1;
+        h->have_step = true;
+        h->have_force = h->write_force;
+        k += len;
+    }
+    return SPH_OK;
+}
+
 // map[d] = device row that lands at row d when rows are stably sorted by start-of-step hash16.
 // Leaves the bucket start offsets (65537 entries) in h->h16_cells.
 int build_hash16_order(sph_handle *h, bool need_map)
@@ -393,15 +468,15 @@ int build_hash16_order(sph_handle *h, bool need_map)
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
     CK(cudaMemsetAsync(h->h16_cells, 0, sizeof(uint32_t) * 65540, s));
-    CK(cudaMemsetAsync(&h->ctr->aux[0], 0, sizeof(uint32_t), s));
+    k_scan_arm<<<1, 32, 0, s>>>(&h->ctr->aux[0], &h->ctr->epoch);
+    CK_LAUNCH();
     if (n) {
         k_hash16_hist<<<blocks_for(n, IO_THREADS), IO_THREADS, 0, s>>>(h->hash16, n, h->h16_cells,
                                                                      need_map ? h->cell_rank : nullptr);
         CK_LAUNCH();
     }
-    ++h->epoch;
     k_scan_exclusive<<<32, SCAN_THREADS, 0, s>>>(h->h16_cells, h->const_65536, h->tile_state, &h->ctr->aux[0],
-                                                h->epoch);
+                                                &h->ctr->epoch);
     CK_LAUNCH();
     if (need_map && n) {
         k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->h16_cells,
@@ -515,6 +590,8 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     nh->forces_cfg = 2;  // 128 threads, <= 48 registers: the pass is latency-bound, occupancy wins
     if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_DENSITY_CFG")) nh->density_cfg = std::atoi(e);
+    if (const char *e = std::getenv("SPH_B200_GRAPH")) nh->graph_enabled = std::atoi(e) != 0;
+    std::memset(&nh->graph_key, 0, sizeof nh->graph_key);
 
     const size_t cap = (size_t)capacity;
     for (int b = 0; b < 2; ++b) {
@@ -569,6 +646,7 @@ int sph_destroy(sph_handle *h)
     for (int k = 0; k < 2; ++k)
         if (h->peer_mailbox[k]) cudaIpcCloseMemHandle(h->peer_mailbox[k]);
     cudaFree(h->mailbox);
+    drop_graphs(h);
     if (h->pinned_rows) cudaFreeHost(h->pinned_rows);
     if (h->ev_rows) cudaEventDestroy(h->ev_rows);
     for (auto &pe : h->ev_pool)
@@ -769,6 +847,7 @@ int sph_step(sph_handle *h, float dt, int nsteps)
     if (nsteps < 0) return fail(h, SPH_ERR_INVALID, "nsteps must be >= 0");
     if (!(dt > 0.f)) dt = h->settings.dt;  // SPHSystem::update's fixed step (src/SPHSystem.cpp:113)
     if (h->n == 0) return SPH_OK;
+    if (h->graph_enabled && !h->timing && !h->slab_mode) return step_graphs(h, dt, nsteps);
     for (int k = 0; k < nsteps; ++k) {
         rc = step_once(h, dt);
         if (rc) return rc;
@@ -1208,7 +1287,6 @@ int sph_slab_step_forces(sph_handle *h, float dt)
     if (!(dt > 0.f)) dt = h->settings.dt;
     const uint32_t n = (uint32_t)h->n;
     if (n) {
-        cudaStream_t s = h->stream;
         rc = launch_forces_integrate(h, n, dt, FI_STEP);
         if (rc) return rc;
         h->parity ^= 1;  // the integration accumulated the next step's box into the other slot

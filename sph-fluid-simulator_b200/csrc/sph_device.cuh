@@ -50,6 +50,7 @@ struct StepCounters {
     uint32_t clamped;     // particles clamped into the grid this step
     uint32_t aux[4];
     uint32_t heavy[2];    // particles deferred to the warp-cooperative density / force kernels
+    uint32_t epoch;       // tag of the current scan's tile states; bumped on the device so a captured step replays
 };
 
 // Settings + derived constants, passed to kernels by value.

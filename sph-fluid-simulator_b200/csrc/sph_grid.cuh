@@ -199,6 +199,7 @@ k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, int
         if (threadIdx.x == 0) {
             *gd = s_g;
             ctr->ticket = 0;
+            ++ctr->epoch;
             ctr->clamped = 0;
             ctr->heavy[0] = ctr->heavy[1] = 0;
             int *nb = ctr->bbox[parity ^ 1];
@@ -245,11 +246,12 @@ __device__ __forceinline__ unsigned long long scan_pack(uint32_t epoch, uint32_t
 
 // In-place exclusive scan of data[0 .. n) where n = *n_ptr + 1. Tiles are handed out by an atomic
 // ticket so a tile only ever waits on tiles that are already running; tile_state words carry an
-// epoch so they never need clearing between steps.
+// epoch (device-resident, bumped by whatever arms the scan) so they never need clearing between steps.
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_exclusive(uint32_t *__restrict__ data, const uint32_t *__restrict__ n_ptr,
-                 unsigned long long *tile_state, uint32_t *ticket, uint32_t epoch)
+                 unsigned long long *tile_state, uint32_t *ticket, const uint32_t *__restrict__ epoch_ptr)
 {
+    const uint32_t epoch = *epoch_ptr;
     __shared__ uint32_t s_tile, s_excl;
     __shared__ uint32_t s_wsum[SCAN_THREADS / 32];
     const uint32_t n = *n_ptr + 1;
@@ -328,6 +330,12 @@ k_scan_exclusive(uint32_t *__restrict__ data, const uint32_t *__restrict__ n_ptr
         }
         __syncthreads();
     }
+}
+
+// Arms a scan outside the step (hash16 ordering): fresh ticket, fresh epoch.
+__global__ void k_scan_arm(uint32_t *ticket, uint32_t *epoch)
+{
+    if (threadIdx.x == 0) { *ticket = 0; ++*epoch; }
 }
 
 // ---- placement and stable order -------------------------------------------------------------

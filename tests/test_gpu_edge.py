@@ -149,6 +149,42 @@ def test_clump_takes_the_warp_cooperative_kernels(sph, oracle):
         assert_bit_equal(runs[1][0][k], got[k], f"second run: {k}")
 
 
+def test_captured_steps_replay_the_same_bits():
+    """sph_step replays CUDA graphs of 1 and 16 captured steps; SPH_B200_GRAPH=0 launches every kernel
+    from the host. 37 = 2 x 16 + 5 steps, then a settings change (new key), an upload and 3 more."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import sph_b200 as S
+from conftest import load_golden
+g = load_golden("cube20_step200.npz")
+s = S.default_settings()
+sim = S.Sim(s, capacity=len(g["pos0"])); sim.upload(g["pos0"], g["vel0"])
+sim.step(37)
+a = sim.download(S.ORDER_ID)
+s.viscosity = 1.5; sim.set_settings(s); sim.step(1); sim.step(2)
+b = sim.download(S.ORDER_ID)
+sim.upload(g["pos0"][:5000], g["vel0"][:5000]); sim.step(3)
+c = sim.download(S.ORDER_ID)
+st = sim.stats()
+np.savez(sys.argv[1], steps=st.steps, launches=sim.launch_count, **{f"{n}_{k}": v for n, d in (("a", a), ("b", b), ("c", c)) for k, v in d.items()})
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        outs = []
+        for graph in ("1", "0"):
+            env = dict(os.environ)
+            env["SPH_B200_GRAPH"] = graph
+            f = os.path.join(d, f"g{graph}.npz")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=env)
+            outs.append(dict(np.load(f)))
+    assert int(outs[0]["steps"]) == int(outs[1]["steps"]) == 3
+    assert int(outs[0]["launches"]) == int(outs[1]["launches"])
+    for k in outs[1]:
+        if k not in ("steps", "launches"):
+            assert_bit_equal(outs[0][k], outs[1][k], f"graph replay vs host launches: {k}")
+
+
 def test_errors_are_reported_not_thrown(sph):
     s = sph.default_settings()
     sim = sph.Sim(s, capacity=10)
