@@ -58,6 +58,15 @@ def weak_scaling_block(g):
     return dict(name=f"weak-scaling-8M-per-gpu-x{g}", h=h, sep=sep, dims=(nx, ny, nz), origin=origin, seed=1024)
 
 
+def dam_break_16m(g):
+    """Config 2: 16 M dam break, the same field for any number of GPUs (strong scaling)."""
+    h = 0.03
+    sep = h * 16.0 / 15.0
+    nx, ny, nz = 160, 256, 392
+    origin = ((h - 8.0) + sep, h * 5.0 / 3.0, -nz * sep / 2.0)
+    return dict(name="dam-break-16M", h=h, sep=sep, dims=(nx, ny, nz), origin=origin, seed=1024, scaling="strong")
+
+
 def measured_traffic(kernel):
     """DRAM bytes per launch of a kernel from the committed ncu --set full capture of this workload
     (profiles/r01_traffic.json, written by tools/ncu_traffic.py), or None."""
@@ -312,7 +321,8 @@ def run_single_gpu(args):
 
 def run_multi_gpu(args):
     slab = __import__("importlib").import_module("sph-fluid-simulator_b200.slab")
-    slab.bench_weak_scaling(args, weak_scaling_block, METRIC, UNIT, ClockSampler, peaks)
+    scene_fn = dam_break_16m if args.workload == "dam-break-16M" else weak_scaling_block
+    slab.bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks)
 
 
 def main():
@@ -331,12 +341,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak-base", action="store_true", help="skip the single-GPU run of the per-GPU workload at N>1")
-    ap.add_argument("--workload", default="auto", choices=["auto", "dam-break-1M", "weak"],
-                    help="auto: config 1 at N=1, config 3 (weak scaling, 8 M particles per GPU) at N>1")
+    ap.add_argument("--workload", default="auto", choices=["auto", "dam-break-1M", "weak", "dam-break-16M"],
+                    help="auto: config 1 at N=1, config 3 (weak scaling, 8 M particles per GPU) at N>1; "
+                         "dam-break-16M: config 2 through the slab driver (strong scaling, any N)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
-    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1 and args.workload != "weak":
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1 and args.workload not in ("weak", "dam-break-16M"):
         return run_single_gpu(args)
     return run_multi_gpu(args)
 

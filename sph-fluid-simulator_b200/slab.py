@@ -636,10 +636,10 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": scene.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": scene["name"], "particles": n_total, "particles_per_gpu": owned_list,
                        "h": scene["h"], "dt": s.dt, "lattice": [nx, ny, nz], "settle_steps": args.settle,
-                       "l2": "state per GPU (>= 8 M particles, ~1 GB touched per step) is larger than the 126 MB L2; "
+                       "l2": f"state per GPU ({n_total // world} particles, ~{292 * (n_total // world) / 1e9:.2f} GB touched per step) is larger than the 126 MB L2; "
                              "L2 flushed once before the timed region",
                        "decomposition": "x slabs; per step: migrants, 1-cell ghost halo and halo densities go to the adjacent "
                                         "ranks with device-resident counts and no host sync; transport = " + transport +
