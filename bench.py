@@ -254,6 +254,18 @@ def run_single_gpu(args):
     lib = S.load_library()
     fptr = mats_t.numpy().ctypes.data_as(C.POINTER(C.c_float))
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    # Secondary figure: the simulation stays resident (the SPHSystem class surface) and every step
+    # only reads back what the renderer draws — model matrices (64 B/particle) or float4 positions.
+    resident = {}
+    for name, fn, floats in (("mat4_transforms", lib.sph_write_transforms, 16), ("float4_positions", lib.sph_read_positions, 4)):
+        for k in range(2 + e2e_steps):
+            if k == 2:
+                t0 = time.perf_counter()
+            sim.step(1)
+            rc = fn(sim.handle, fptr)
+            assert rc == 0, lib.sph_last_error(sim.handle)
+        resident[name] = {"value": n * e2e_steps / (time.perf_counter() - t0), "unit": UNIT,
+                          "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * floats * n}
     for _ in range(2):
         rc = lib.sph_update_particles_aos(sim.handle, rows.ctypes.data_as(C.c_void_p), fptr, n, C.c_float(s.dt))
         assert rc == 0, lib.sph_last_error(sim.handle)
@@ -309,7 +321,8 @@ def run_single_gpu(args):
                    "ms_per_step_p50": float(np.median(step_ms)), "ms_per_step_max": float(step_ms.max())},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60 * n, "d2h_bytes_per_step": 124 * n,
-                "steps": e2e_steps, "call": "sph_update_particles_aos (60-byte Particle rows + mat4 transforms, pinned host memory)"},
+                "steps": e2e_steps, "call": "sph_update_particles_aos (60-byte Particle rows + mat4 transforms, pinned host memory)",
+                "resident_simulation_with_renderer_readout": resident},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
