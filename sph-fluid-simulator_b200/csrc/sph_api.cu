@@ -335,7 +335,20 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
     } else if (mode == FI_STEP_WRITE_FORCE) {
         LAUNCH_FI(128, 10, FI_STEP_WRITE_FORCE);
     } else {
+#define LAUNCH_FT(T, B, CAPR)                                                                                     \
+    do {                                                                                                         \
+        auto kern = k_forces_tile<T, B, FI_STEP, CAPR>;                                                          \
+        static bool armed = false;                                                                               \
+        if (!armed) {                                                                                            \
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * CAPR));              \
+            armed = true;                                                                                        \
+        }                                                                                                        \
+        kern<<<blocks_for(n, T), T, 32 * CAPR, s>>>(h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist,   \
+                                                    h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1], h->vel[in ^ 1], \
+                                                    h->force, h->ctr, h->parity ^ 1, h->map);                     \
+    } while (0)
         switch (h->forces_cfg) {
+        case 6: LAUNCH_FT(128, 5, 1408); break;  // shared-memory staged neighbourhoods: measured 2-4x slower
         case 1: LAUNCH_FI(128, 8, FI_STEP); break;
         case 3: LAUNCH_FI(64, 16, FI_STEP); break;
         case 4: LAUNCH_FI(256, 4, FI_STEP); break;

@@ -185,6 +185,31 @@ np.savez(sys.argv[1], steps=st.steps, launches=sim.launch_count, **{f"{n}_{k}": 
             assert_bit_equal(outs[0][k], outs[1][k], f"graph replay vs host launches: {k}")
 
 
+def test_tile_staged_force_kernel_returns_the_same_bits():
+    """SPH_B200_FORCES_CFG=6 stages each block's neighbourhoods in shared memory (kept as a measured
+    alternative). Same lists, same order, so the same bits as the default kernel."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import sph_b200 as S
+from conftest import load_golden
+g = load_golden("cube20_step200.npz")
+sim = S.Sim(S.default_settings(), capacity=len(g["pos0"])); sim.upload(g["pos0"], g["vel0"]); sim.step(5)
+np.savez(sys.argv[1], **sim.download(S.ORDER_ID))
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        outs = []
+        for cfg in ("0", "6"):
+            env = dict(os.environ)
+            env["SPH_B200_FORCES_CFG"] = cfg
+            f = os.path.join(d, f"f{cfg}.npz")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=env)
+            outs.append(dict(np.load(f)))
+    for k in ("pos", "vel", "force", "density"):
+        assert_bit_equal(outs[1][k], outs[0][k], f"tile-staged forces: {k}")
+
+
 def test_errors_are_reported_not_thrown(sph):
     s = sph.default_settings()
     sim = sph.Sim(s, capacity=10)
