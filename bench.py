@@ -86,16 +86,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled during the timed region: NVML from a thread every 50 ms
+    (a sample costs microseconds, so even a quarter-second region gets several), nvidia-smi -lms as the
+    fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []      # nvidia-smi text rows
+        self.samples = []   # (sm MHz, reasons bitmask) from NVML
         self.proc = None
         self.index = index
+        self.nvml = None
+        self.dev = None
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            if os.environ.get("SPH_CLOCK_SAMPLER", "nvml") != "nvml":
+                raise ImportError("nvidia-smi sampler requested")
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.dev = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001 - older torch without .uuid, or CUDA_VISIBLE_DEVICES remapping unknown
+                self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    def _sample(self):
+        try:
+            mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.dev, self.nvml.NVML_CLOCK_SM))
+            try:
+                bits = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
+            except AttributeError:
+                bits = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev))
+            self.samples.append((mhz, bits))
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(0.05)
 
     def start(self):
+        if self.nvml:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -109,20 +154,30 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self._sample()  # the region has just ended: the GPU is still at its load clocks
+            self._stop.set()
+            if self._thread:
+                self._thread.join(timeout=1.0)
+            sm = [m for m, _ in self.samples]
+            bits = 0
+            for _, b in self.samples:
+                bits |= b
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(k for k, v in self.BITS.items() if bits & v), "samples": len(sm), "source": "nvml"}
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
-            for k, nme in enumerate(names):
+            for k, nme in enumerate(self.NAMES):
                 if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def reference_step_fn():

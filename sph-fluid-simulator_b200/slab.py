@@ -605,25 +605,36 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
         m = read_back()
         k_e2e = max(2, min(args.e2e_steps, 5))
         t_e2e = 0.0
+        iter_ms = []
         import time
-        for k in range(k_e2e + 1):
+        e2e_warm = 2  # untimed iterations: first-touch of the pinned buffers, lazy transport set-up
+        for k in range(k_e2e + e2e_warm):
             if world > 1:
                 dist.barrier()
             t0 = time.perf_counter()
             rc = sim.lib.sph_upload(sim.handle, m, pp, pv, pi_)   # pinned host rows -> device
             if rc:
                 raise RuntimeError(sim.lib.sph_last_error(sim.handle).decode())
+            if driver.profile:
+                sim.sync(); t1 = time.perf_counter()
             driver.step(s.dt)
+            if driver.profile:
+                sim.sync(); t2 = time.perf_counter()
             m = read_back()                                       # owned rows -> pinned host
+            if driver.profile:
+                print(f"[rank {rank}] e2e iteration {k}: upload {1e3 * (t1 - t0):.2f} ms, step {1e3 * (t2 - t1):.2f} ms, "
+                      f"download {1e3 * (time.perf_counter() - t2):.2f} ms", file=sys.stderr, flush=True)
             if world > 1:
                 dist.barrier()
-            if k > 0:  # first iteration is warm-up
+            iter_ms.append(1e3 * (time.perf_counter() - t0))
+            if k >= e2e_warm:
                 t_e2e += time.perf_counter() - t0
         tt = torch.tensor([t_e2e], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_total * k_e2e / float(tt.item()), "unit": UNIT, "steps": k_e2e,
                "h2d_bytes_per_step": 28 * n_total, "d2h_bytes_per_step": 28 * n_total,
+               "iteration_ms_rank0": [round(v, 2) for v in iter_ms],
                "call": "per rank: sph_upload(pos, vel, id in pinned host memory) -> slab step (general path) -> "
                        "sph_slab_download_owned(pos, vel, id into pinned host memory)"}
     if driver.profile:
