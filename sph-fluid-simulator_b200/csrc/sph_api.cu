@@ -69,6 +69,7 @@ struct sph_handle {
     uint64_t p2p_H = 0, p2p_M = 0;
     uint32_t p2p_epoch = 0;
     int forces_cfg = 0, density_cfg = 0;
+    bool tile_armed = false;  // k_forces_tile's dynamic shared memory limit has been raised
     unsigned long long *slab_counts = nullptr;  // SLAB_MAX_RANKS counters + cursors
     uint32_t *cells = nullptr;
     uint32_t max_cells = 0;
@@ -338,10 +339,9 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
 #define LAUNCH_FT(T, B, CAPR)                                                                                     \
     do {                                                                                                         \
         auto kern = k_forces_tile<T, B, FI_STEP, CAPR>;                                                          \
-        static bool armed = false;                                                                               \
-        if (!armed) {                                                                                            \
+        if (!h->tile_armed) { /* per handle: the attribute belongs to the handle's device */                    \
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * CAPR));              \
-            armed = true;                                                                                        \
+            h->tile_armed = true;                                                                                \
         }                                                                                                        \
         kern<<<blocks_for(n, T), T, 32 * CAPR, s>>>(h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist,   \
                                                     h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1], h->vel[in ^ 1], \
