@@ -5,6 +5,7 @@
 // (--fmad=false is part of the parity contract, see sph_device.cuh).
 #include "../../include/sph_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -69,6 +70,11 @@ struct sph_handle {
     uint64_t p2p_H = 0, p2p_M = 0;
     uint32_t p2p_epoch = 0;
     int forces_cfg = 0, density_cfg = 0;
+    // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
+    // are in the cell order of the last build, i.e. from a slab force step until anything else touches them.
+    bool edge_ok = false;        // rows [0, n) are in the cell order h->cells describes
+    bool edge_all = true;        // this step's scans look at every row
+    uint64_t edge_sorted = 0;    // rows in cell order when this step began (arrivals are appended behind them)
     bool tile_armed = false;  // k_forces_tile's dynamic shared memory limit has been raised
     unsigned long long *slab_counts = nullptr;  // SLAB_MAX_RANKS counters + cursors
     uint32_t *cells = nullptr;
@@ -249,6 +255,7 @@ int compute_bbox(sph_handle *h)
 // h->n shrinks to the surviving row count.
 int build_grid(sph_handle *h)
 {
+    h->edge_ok = false;  // rows move; a slab force step declares them ordered again
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
     k_plan_zero<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
@@ -504,6 +511,7 @@ int build_hash16_order(sph_handle *h, bool need_map)
 
 int after_upload(sph_handle *h, uint64_t n)
 {
+    h->edge_ok = false;
     h->n = n;
     h->steps = 0;
     h->have_state = true;
@@ -1183,6 +1191,7 @@ int sph_slab_pack(sph_handle *h, const int32_t *cuts, int world, int self, void 
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
     h->slab_fast = false;
+    h->edge_ok = false;
     return SPH_OK;
 }
 
@@ -1208,6 +1217,7 @@ int sph_slab_append(sph_handle *h, const void *dev_rows, uint64_t nrows, int kin
     h->n += nrows;
     h->have_state = true;
     h->have_step = false;
+    h->edge_ok = false;
     return SPH_OK;
 }
 
@@ -1308,6 +1318,7 @@ int sph_slab_step_forces(sph_handle *h, float dt)
     h->launches += 2;
     ++h->steps;
     h->have_step = true;
+    h->edge_ok = true;
     return SPH_OK;
 }
 
@@ -1368,6 +1379,21 @@ int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, u
 
 // ---- sync-free slab path: fixed-size messages to the adjacent ranks, no host synchronisation ----
 
+// Start of a sync-free slab step: decide whether its two scans may be confined to the edge layers.
+static void begin_edge_scans(sph_handle *h)
+{
+    h->edge_all = !h->edge_ok;
+    h->edge_sorted = h->n;
+    h->edge_ok = false;  // consumed: rows get dropped and appended from here on
+}
+
+// Grid of the edge scans (grid-stride kernels): enough blocks for every row when the scan is not confined.
+static unsigned edge_blocks(const sph_handle *h)
+{
+    const unsigned full = blocks_for(h->n, SLAB_THREADS);
+    return h->edge_all ? full : std::min(full, (unsigned)h->num_sms * 8u);
+}
+
 int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next, uint64_t cap_rows,
                         void *dev_send_left, void *dev_send_right)
 {
@@ -1382,11 +1408,12 @@ int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, 
     CK(cudaMemsetAsync(&h->ctr->aux[3], 0, sizeof(uint32_t), s));
     if (dev_send_left) CK(cudaMemsetAsync(dev_send_left, 0xFF, cap_rows * 32, s));
     if (dev_send_right) CK(cudaMemsetAsync(dev_send_right, 0xFF, cap_rows * 32, s));
+    begin_edge_scans(h);
     if (h->n) {
-        k_slab_fast_begin<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+        k_slab_fast_begin<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dev_send_left ? lo : -0x7fffffff - 1,
             dev_send_right ? hi : 0x7fffffff, lo_prev, hi_next, (uint32_t)cap_rows, (float4 *)dev_send_left,
-            (float4 *)dev_send_right, cur, &h->ctr->aux[3]);
+            (float4 *)dev_send_right, cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all);
         CK_LAUNCH();
     }
     h->slab_fast = true;
@@ -1432,10 +1459,11 @@ int sph_slab_fast_halo(sph_handle *h, int32_t lo, int32_t hi, uint64_t cap_rows,
     if (dev_send_left) CK(cudaMemsetAsync(dev_send_left, 0xFF, cap_rows * 32, s));
     if (dev_send_right) CK(cudaMemsetAsync(dev_send_right, 0xFF, cap_rows * 32, s));
     if (h->n) {
-        k_slab_fast_halo<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+        k_slab_fast_halo<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dev_send_left != nullptr,
             dev_send_right != nullptr, (uint32_t)cap_rows, (float4 *)dev_send_left, (float4 *)dev_send_right,
-            h->halo_rows[0], h->halo_rows[1], h->slab_counts + 2 * SLAB_MAX_RANKS, &h->ctr->aux[3]);
+            h->halo_rows[0], h->halo_rows[1], h->slab_counts + 2 * SLAB_MAX_RANKS, &h->ctr->aux[3], h->gd, h->cells,
+            h->ctr, (uint32_t)h->edge_sorted, h->edge_all);
         CK_LAUNCH();
     }
     h->fast_halo_cap = cap_rows;
@@ -1555,10 +1583,11 @@ int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, i
     float4 *dst[2] = {nullptr, nullptr};
     for (int side = 0; side < 2; ++side)
         if (h->peer_mailbox[side]) dst[side] = (float4 *)peer_slot(h, side, L.mig[side ^ 1][b]);
+    begin_edge_scans(h);
     if (h->n) {
-        k_slab_fast_begin<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+        k_slab_fast_begin<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dst[0] ? lo : -0x7fffffff - 1, dst[1] ? hi : 0x7fffffff,
-            lo_prev, hi_next, (uint32_t)h->p2p_M, dst[0], dst[1], cur, &h->ctr->aux[3]);
+            lo_prev, hi_next, (uint32_t)h->p2p_M, dst[0], dst[1], cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all);
         CK_LAUNCH();
     }
     for (int side = 0; side < 2; ++side)
@@ -1619,9 +1648,10 @@ int sph_slab_p2p_halo(sph_handle *h, int32_t lo, int32_t hi)
     for (int side = 0; side < 2; ++side)
         if (h->peer_mailbox[side]) dst[side] = (float4 *)peer_slot(h, side, L.halo[side ^ 1][b]);
     if (h->n) {
-        k_slab_fast_halo<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
+        k_slab_fast_halo<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dst[0] != nullptr, dst[1] != nullptr,
-            (uint32_t)h->p2p_H, dst[0], dst[1], h->halo_rows[0], h->halo_rows[1], cur, &h->ctr->aux[3]);
+            (uint32_t)h->p2p_H, dst[0], dst[1], h->halo_rows[0], h->halo_rows[1], cur, &h->ctr->aux[3], h->gd, h->cells,
+            h->ctr, (uint32_t)h->edge_sorted, h->edge_all);
         CK_LAUNCH();
     }
     for (int side = 0; side < 2; ++side)

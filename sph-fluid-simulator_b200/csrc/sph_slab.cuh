@@ -107,76 +107,131 @@ k_slab_append(const float4 *__restrict__ rows, uint32_t nrows, uint32_t first, b
 // Violation bits accumulated in StepCounters::aux[3] and read back one step late.
 constexpr uint32_t SLAB_ERR_MIGRANT_OVERFLOW = 1u, SLAB_ERR_HALO_OVERFLOW = 2u, SLAB_ERR_NOT_ADJACENT = 4u;
 
-// One pass over the rows: last step's ghosts are dropped; owned rows whose cell.x left [lo, hi)
+// ---- edge scans ---------------------------------------------------------------------------------
+//
+// Between two grid builds the rows stay in the start-of-step cell order (x slowest), so the rows of
+// the slab's outer x-layers are two contiguous ranges delimited by the cell-start table, and rows
+// appended since (arrivals) are a third one at the end. As long as no particle crosses more than
+// one cell per step (StepCounters::fast_x, set by the integration), migrants, stale ghosts and the
+// next halo can only be found there: the sync-free step scans ~2 % of the rows instead of all of
+// them, twice. `all` (rows not in cell order: after an upload or a general-path step) or a fast
+// particle fall back to every row.
+struct EdgeScan {
+    uint32_t first[3], len[3];
+};
+
+// Rows whose start-of-step cell.x <= lo + depth - 1 or >= hi - depth, plus the rows [sorted, n).
+__device__ __forceinline__ void edge_scan_plan(EdgeScan &e, const GridDesc &g, const uint32_t *__restrict__ starts,
+                                               uint32_t n, uint32_t sorted, int lo, int hi, int depth, bool all)
+{
+    sorted = min(sorted, n);
+    uint32_t l_end = sorted, r_begin = sorted;
+    if (!all) {
+        const long long gl = min(max((long long)lo + depth - 1 - g.ox, 1LL), (long long)g.nx - 2);  // last left layer
+        const long long gr = min(max((long long)hi - depth - g.ox, 1LL), (long long)g.nx - 2);      // first right layer
+        if (gr > gl) {
+            l_end = min(starts[(uint32_t)(gl + 1) * g.sx], sorted);
+            r_begin = max(min(starts[(uint32_t)gr * g.sx], sorted), l_end);
+        }
+    }
+    e.first[0] = 0;       e.len[0] = l_end;
+    e.first[1] = r_begin; e.len[1] = sorted - r_begin;
+    e.first[2] = sorted;  e.len[2] = n - sorted;
+}
+
+__device__ __forceinline__ uint32_t edge_scan_row(const EdgeScan &e, uint32_t t)
+{
+    if (t < e.len[0]) return t;
+    t -= e.len[0];
+    if (t < e.len[1]) return e.first[1] + t;
+    return e.first[2] + (t - e.len[1]);
+}
+
+// One pass over the edge rows: last step's ghosts are dropped; owned rows whose cell.x left [lo, hi)
 // are copied to the left / right migrant message (pre-filled with dropped rows by the caller)
 // and dropped here. cur[0], cur[1] = message cursors (start at 0). A row that would have to travel
 // further than the adjacent rank, or does not fit, raises a violation bit and stays put.
 __global__ void __launch_bounds__(SLAB_THREADS)
 k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int lo, int hi,
                   int lo_prev, int hi_next, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
-                  unsigned long long *__restrict__ cur, uint32_t *__restrict__ err)
+                  unsigned long long *__restrict__ cur, uint32_t *__restrict__ err, const GridDesc *__restrict__ gd,
+                  const uint32_t *__restrict__ starts, const StepCounters *__restrict__ ctr, bool all)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 p = pos[i];
-    const uint32_t w = __float_as_uint(p.w);
-    if (w == W_DROP) return;
-    bool drop = (w & W_GHOST) != 0u;
-    if (!drop) {
-        const int cx = cell_of(p.x, h);
-        const int side = cx < lo ? 0 : (cx >= hi ? 1 : -1);
-        if (side >= 0) {
-            if ((side == 0 && cx < lo_prev) || (side == 1 && cx >= hi_next)) {
-                atomicOr(err, SLAB_ERR_NOT_ADJACENT);
-            } else {
-                const unsigned long long k = atomicAdd(&cur[side], 1ull);
-                if (k >= cap) {
-                    atomicOr(err, SLAB_ERR_MIGRANT_OVERFLOW);
+    __shared__ EdgeScan s_e;
+    if (threadIdx.x == 0) edge_scan_plan(s_e, *gd, starts, n, n, lo, hi, 1, all || ctr->fast_x != 0u);
+    __syncthreads();
+    const EdgeScan e = s_e;
+    const uint32_t total = e.len[0] + e.len[1] + e.len[2];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const uint32_t i = edge_scan_row(e, t);
+        float4 p = pos[i];
+        const uint32_t w = __float_as_uint(p.w);
+        if (w == W_DROP) continue;
+        bool drop = (w & W_GHOST) != 0u;
+        if (!drop) {
+            const int cx = cell_of(p.x, h);
+            const int side = cx < lo ? 0 : (cx >= hi ? 1 : -1);
+            if (side >= 0) {
+                if ((side == 0 && cx < lo_prev) || (side == 1 && cx >= hi_next)) {
+                    atomicOr(err, SLAB_ERR_NOT_ADJACENT);
                 } else {
-                    float4 *dst = side == 0 ? send_l : send_r;
-                    float4 v = vel[i];
-                    v.w = 0.f;
-                    dst[2 * k] = p;
-                    dst[2 * k + 1] = v;
-                    drop = true;
+                    const unsigned long long k = atomicAdd(&cur[side], 1ull);
+                    if (k >= cap) {
+                        atomicOr(err, SLAB_ERR_MIGRANT_OVERFLOW);
+                    } else {
+                        float4 *dst = side == 0 ? send_l : send_r;
+                        float4 v = vel[i];
+                        v.w = 0.f;
+                        dst[2 * k] = p;
+                        dst[2 * k + 1] = v;
+                        drop = true;
+                    }
                 }
             }
         }
-    }
-    if (drop) {
-        p.w = __uint_as_float(W_DROP);
-        pos[i] = p;
+        if (drop) {
+            p.w = __uint_as_float(W_DROP);
+            pos[i] = p;
+        }
     }
 }
 
-// Both halo messages in one pass: owned rows of x-cell lo go left, of x-cell hi-1 go right (a
-// one-cell slab sends its rows both ways). cur[2], cur[3] = cursors; rows_l / rows_r remember the
-// source rows so the densities can follow in the same order.
+// Both halo messages in one pass over the edge rows (two layers deep: a row of layer lo + 1 may have
+// moved into layer lo) and the arrivals appended at [sorted, n): owned rows of x-cell lo go left, of
+// x-cell hi-1 go right (a one-cell slab sends its rows both ways). cur[2], cur[3] = cursors;
+// rows_l / rows_r remember the source rows so the densities can follow in the same order.
 __global__ void __launch_bounds__(SLAB_THREADS)
 k_slab_fast_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int lo, int hi,
                  bool has_left, bool has_right, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
                  uint32_t *__restrict__ rows_l, uint32_t *__restrict__ rows_r, unsigned long long *__restrict__ cur,
-                 uint32_t *__restrict__ err)
+                 uint32_t *__restrict__ err, const GridDesc *__restrict__ gd, const uint32_t *__restrict__ starts,
+                 const StepCounters *__restrict__ ctr, uint32_t sorted, bool all)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float4 p = pos[i];
-    const uint32_t w = __float_as_uint(p.w);
-    if (w == W_DROP || (w & W_GHOST)) return;
-    const int cx = cell_of(p.x, h);
-    const bool to_l = has_left && cx == lo, to_r = has_right && cx == hi - 1;
-    if (!to_l && !to_r) return;
-    float4 v = vel[i];
-    v.w = 0.f;
-    if (to_l) {
-        const unsigned long long k = atomicAdd(&cur[2], 1ull);
-        if (k < cap) { send_l[2 * k] = p; send_l[2 * k + 1] = v; rows_l[k] = i; }
-        else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
-    }
-    if (to_r) {
-        const unsigned long long k = atomicAdd(&cur[3], 1ull);
-        if (k < cap) { send_r[2 * k] = p; send_r[2 * k + 1] = v; rows_r[k] = i; }
-        else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
+    __shared__ EdgeScan s_e;
+    if (threadIdx.x == 0) edge_scan_plan(s_e, *gd, starts, n, sorted, lo, hi, 2, all || ctr->fast_x != 0u);
+    __syncthreads();
+    const EdgeScan e = s_e;
+    const uint32_t total = e.len[0] + e.len[1] + e.len[2];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const uint32_t i = edge_scan_row(e, t);
+        const float4 p = pos[i];
+        const uint32_t w = __float_as_uint(p.w);
+        if (w == W_DROP || (w & W_GHOST)) continue;
+        const int cx = cell_of(p.x, h);
+        const bool to_l = has_left && cx == lo, to_r = has_right && cx == hi - 1;
+        if (!to_l && !to_r) continue;
+        float4 v = vel[i];
+        v.w = 0.f;
+        if (to_l) {
+            const unsigned long long k = atomicAdd(&cur[2], 1ull);
+            if (k < cap) { send_l[2 * k] = p; send_l[2 * k + 1] = v; rows_l[k] = i; }
+            else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
+        }
+        if (to_r) {
+            const unsigned long long k = atomicAdd(&cur[3], 1ull);
+            if (k < cap) { send_r[2 * k] = p; send_r[2 * k + 1] = v; rows_r[k] = i; }
+            else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
+        }
     }
 }
 

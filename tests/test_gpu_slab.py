@@ -27,14 +27,21 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _scene(S):
-    """Dense interacting state with hash-collision double counts: the 20^3 golden cube at step 200."""
+def _scene(S, jet=False):
+    """Dense interacting state with hash-collision double counts: the 20^3 golden cube at step 200.
+    jet: a few particles in the middle of the cube cross more than one cell per step along x, which
+    the sync-free steps must notice (they otherwise only scan the slab's edge layers)."""
     g = load_golden("cube20_step200.npz")
     s = S.default_settings()
-    return s, g["pos0"], g["vel0"]
+    pos, vel = g["pos0"].copy(), g["vel0"].copy()
+    if jet:
+        mid = np.argsort(np.abs(pos[:, 0] - np.median(pos[:, 0])))[:24]
+        vel[mid[:12], 0] = 1.3 * s.h / s.dt
+        vel[mid[12:], 0] = -1.3 * s.h / s.dt
+    return s, pos, vel
 
 
-def _worker(rank, world, port, backend, steps, fast, out_dir):
+def _worker(rank, world, port, backend, steps, fast, out_dir, jet=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import sph_b200 as S
@@ -42,7 +49,7 @@ def _worker(rank, world, port, backend, steps, fast, out_dir):
     dev = rank if backend == "nccl" else 0
     torch.cuda.set_device(dev)
     dist.init_process_group(backend, rank=rank, world_size=world)
-    s, pos, vel = _scene(S)
+    s, pos, vel = _scene(S, jet)
     n = pos.shape[0]
     ids = np.arange(n, dtype=np.uint32)
     drv, sim = slab.make_gpu_driver(s, 2 * n + 65536, dev, rank, world)  # room for the fixed-size message regions
@@ -74,8 +81,8 @@ def _worker(rank, world, port, backend, steps, fast, out_dir):
     dist.destroy_process_group()
 
 
-def _single_gpu_reference(sph, steps, out_dir):
-    s, pos, vel = _scene(sph)
+def _single_gpu_reference(sph, steps, out_dir, jet=False):
+    s, pos, vel = _scene(sph, jet)
     sim = sph.Sim(s, capacity=pos.shape[0])
     sim.upload(pos, vel)
     sim.step(steps)
@@ -107,6 +114,17 @@ def test_slab_step_is_bit_identical_to_single_gpu_gloo(sph, world, fast):
     with tempfile.TemporaryDirectory() as d:
         want = _single_gpu_reference(sph, steps, d)
         mp.spawn(_worker, args=(world, _free_port(), "gloo", steps, fast, d), nprocs=world, join=True)
+        ranks = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
+    _compare(ranks, want, world)
+
+
+@pytest.mark.parametrize("fast", [True, "p2p"], ids=["syncfree", "peer-mailbox"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_fast_particles_make_the_sync_free_step_scan_every_row(sph, world, fast):
+    steps = 7
+    with tempfile.TemporaryDirectory() as d:
+        want = _single_gpu_reference(sph, steps, d, jet=True)
+        mp.spawn(_worker, args=(world, _free_port(), "gloo", steps, fast, d, True), nprocs=world, join=True)
         ranks = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
     _compare(ranks, want, world)
 
