@@ -86,7 +86,7 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled during the timed region: NVML from a thread every 50 ms
+    """SM clock and throttle reasons sampled during the timed region: NVML from a thread every 100 ms
     (a sample costs microseconds, so even a quarter-second region gets several), nvidia-smi -lms as the
     fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -134,7 +134,7 @@ class ClockSampler:
     def _loop(self):
         while not self._stop.is_set():
             self._sample()
-            self._stop.wait(0.05)
+            self._stop.wait(0.1)
 
     def start(self):
         if self.nvml:

@@ -72,6 +72,7 @@ struct sph_handle {
     int forces_cfg = 0, density_cfg = 0;
     // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
     // are in the cell order of the last build, i.e. from a slab force step until anything else touches them.
+    bool edge_scan_enabled = false;  // SPH_B200_EDGE_SCAN=1 (opt-in: see DESIGN.md §5 for the measurements)
     bool edge_ok = false;        // rows [0, n) are in the cell order h->cells describes
     bool edge_all = true;        // this step's scans look at every row
     uint64_t edge_sorted = 0;    // rows in cell order when this step began (arrivals are appended behind them)
@@ -612,6 +613,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_DENSITY_CFG")) nh->density_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_GRAPH")) nh->graph_enabled = std::atoi(e) != 0;
+    if (const char *e = std::getenv("SPH_B200_EDGE_SCAN")) nh->edge_scan_enabled = std::atoi(e) != 0;
     std::memset(&nh->graph_key, 0, sizeof nh->graph_key);
 
     const size_t cap = (size_t)capacity;
@@ -1382,7 +1384,7 @@ int sph_slab_xcell_histogram(sph_handle *h, int32_t x_cell_lo, uint32_t nbins, u
 // Start of a sync-free slab step: decide whether its two scans may be confined to the edge layers.
 static void begin_edge_scans(sph_handle *h)
 {
-    h->edge_all = !h->edge_ok;
+    h->edge_all = !h->edge_ok || !h->edge_scan_enabled;
     h->edge_sorted = h->n;
     h->edge_ok = false;  // consumed: rows get dropped and appended from here on
 }

@@ -558,8 +558,10 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
         dist.barrier()
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
-    clocks = ClockSampler(local)
-    clocks.start()
+    # rank 0 samples its own GPU; one poller per job keeps NVML out of the other ranks' launch paths
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
     launches0 = sim.launch_count
     stream = driver.e.stream
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -581,7 +583,7 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
         owned_list = [int(o.item()) for o in owned_all]
     else:
         owned_list = [int(owned.item())]
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
 
     # ---- end to end: every step uploads the rank's rows from pinned host memory, steps through the
     # slab driver (general path: an upload resets the resident state) and reads positions and

@@ -118,13 +118,29 @@ def test_slab_step_is_bit_identical_to_single_gpu_gloo(sph, world, fast):
     _compare(ranks, want, world)
 
 
+@pytest.fixture
+def edge_scans():
+    """SPH_B200_EDGE_SCAN=1 for the spawned ranks: the sync-free steps look for migrants and ghosts in
+    the slab's edge x-layers only (opt-in)."""
+    old = os.environ.get("SPH_B200_EDGE_SCAN")
+    os.environ["SPH_B200_EDGE_SCAN"] = "1"
+    yield
+    if old is None:
+        del os.environ["SPH_B200_EDGE_SCAN"]
+    else:
+        os.environ["SPH_B200_EDGE_SCAN"] = old
+
+
 @pytest.mark.parametrize("fast", [True, "p2p"], ids=["syncfree", "peer-mailbox"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_fast_particles_make_the_sync_free_step_scan_every_row(sph, world, fast):
+@pytest.mark.parametrize("jet", [False, True], ids=["calm", "jet"])
+def test_edge_scans_are_bit_identical_and_fall_back_for_fast_particles(sph, edge_scans, world, fast, jet):
+    """jet: a few particles cross more than one cell per step, so an interior row leaves the slab;
+    the integration flags it and the next step scans every row."""
     steps = 7
     with tempfile.TemporaryDirectory() as d:
-        want = _single_gpu_reference(sph, steps, d, jet=True)
-        mp.spawn(_worker, args=(world, _free_port(), "gloo", steps, fast, d, True), nprocs=world, join=True)
+        want = _single_gpu_reference(sph, steps, d, jet=jet)
+        mp.spawn(_worker, args=(world, _free_port(), "gloo", steps, fast, d, jet), nprocs=world, join=True)
         ranks = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
     _compare(ranks, want, world)
 
