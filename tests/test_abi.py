@@ -99,3 +99,34 @@ def test_null_and_bad_arguments_do_not_crash(sph):
     s.h = 0.0
     assert lib.sph_create(ctypes.byref(s), 10, 0, ctypes.byref(out)) != 0
     assert b"h must be" in lib.sph_last_error(None)
+
+
+def test_header_is_plain_c99_and_cxx11(tmp_path):
+    """The boundary is a C ABI: the header must compile as C (not only as C++) with warnings on."""
+    import shutil
+    import subprocess
+    header = os.path.join(ROOT, "include", "sph_b200.h")
+    for compiler, std, ext in (("gcc", "-std=c99", "c"), ("g++", "-std=c++11", "cpp")):
+        exe = "/usr/bin/" + compiler if os.path.exists("/usr/bin/" + compiler) else shutil.which(compiler)
+        src = tmp_path / f"hdr.{ext}"
+        src.write_text(f'#include "{header}"\nint main(void) {{ sph_settings s; (void)s; return SPH_OK; }}\n')
+        subprocess.run([exe, std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", str(src)], check=True)
+
+
+def test_c_example_links_against_the_library(sph, tmp_path):
+    """examples/step_cube.c is the smallest host of the C-ABI; without a GPU it must stop with the
+    library's error message, not fall back to anything."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    libdir = os.path.dirname(sph.binding.LIB_PATH)
+    exe = tmp_path / "step_cube"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-O2", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "step_cube.c"), "-L", libdir, "-lsph_b200", f"-Wl,-rpath,{libdir}",
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    import torch
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "step 1000" in out.stdout, out.stderr
+    else:
+        assert out.returncode == 1 and "sph_create" in out.stderr and "failed" in out.stderr
