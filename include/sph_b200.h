@@ -196,6 +196,11 @@ uint64_t sph_launch_count(const sph_handle *h);
  * n pseudo-random pairs and returns the number of mismatches (expected 0). */
 int sph_selftest_division(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out);
 
+/* Device self-test: the density pass tests one candidate against two rows with packed fp32x2
+ * arithmetic (csrc/sph_physics.cuh, pair_dist2); this checks both halves bit-for-bit against the scalar
+ * (dx*dx + dy*dy) + dz*dz of glm::length2 (src/sph.cpp:57) on n pseudo-random triples (expected 0). */
+int sph_selftest_pair_dist2(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out);
+
 /* Raw CUDA stream of the handle (cudaStream_t as void*), so a caller can order its own work or
  * record events on it. */
 void *sph_stream(sph_handle *h);

@@ -50,6 +50,7 @@ struct sph_handle {
     uint32_t *nlist = nullptr, *ncount = nullptr;  // neighbour lists written by the density pass
     uint2 *cell_rank = nullptr, *slot = nullptr;
     uint32_t *order = nullptr, *map = nullptr;
+    uint32_t *single_list = nullptr;      // rows the pair-walk density kernel left for k_density_single
     uint32_t *inverse = nullptr;          // sorted row of each pre-sort row (slab mode)
     uint32_t *halo_rows[2] = {nullptr, nullptr};  // pre-sort rows packed into each halo message
     uint64_t halo_n[2] = {0, 0};
@@ -116,6 +117,7 @@ struct sph_handle {
     };
     GraphKey graph_key;
     cudaGraphExec_t graphs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [1 | kGraphLong steps][parity]
+    uint64_t graph_launches[2] = {0, 0};  // kernel nodes of a captured 1-step / kGraphLong-step graph (counted at capture)
     bool graph_enabled = true;  // SPH_B200_GRAPH=0 launches every kernel from the host
 
     char err[512] = "";
@@ -141,6 +143,8 @@ int fail(sph_handle *h, int code, const char *fmt, ...)
                         cudaGetErrorString(e_));                                                   \
     } while (0)
 #define CK_LAUNCH() CK(cudaGetLastError())
+// after a kernel launch of the step pipeline: checked and counted (sph_launch_count)
+#define CK_STEP_LAUNCH() do { CK(cudaGetLastError()); ++h->launches; } while (0)
 
 inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -260,20 +264,20 @@ int build_grid(sph_handle *h)
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
     k_plan_zero<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
-    CK_LAUNCH();
+    CK_STEP_LAUNCH();
     k_cell_hist<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->pos[h->cur], n, h->P.h, h->gd, h->cells,
                                                                    h->cell_rank, h->ctr);
-    CK_LAUNCH();
+    CK_STEP_LAUNCH();
     k_scan_exclusive<<<h->num_sms * 4, SCAN_THREADS, 0, s>>>(h->cells, &h->gd->ncells, h->tile_state,
                                                             &h->ctr->ticket, &h->ctr->epoch);
-    CK_LAUNCH();
+    CK_STEP_LAUNCH();
     k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot);
-    CK_LAUNCH();
+    CK_STEP_LAUNCH();
     uint32_t n_sorted = n;
     const uint32_t *n_dev = nullptr;
     if (h->slab_mode) {
         k_publish_rows<<<1, 32, 0, s>>>(h->cells, h->gd, h->ctr);
-        CK_LAUNCH();
+        CK_STEP_LAUNCH();
         if (h->slab_fast) {
             // No host sync: later kernels run over the bound n and skip the dropped tail; the exact
             // count (and the violation bits next to it) reach the host before the next step.
@@ -290,34 +294,51 @@ int build_grid(sph_handle *h)
         k_order_gather<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
             h->slot, h->cell_rank, n_sorted, n_dev, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1],
             h->vel[h->cur ^ 1], h->hash16, h->slab_mode ? h->inverse : nullptr);
-        CK_LAUNCH();
+        CK_STEP_LAUNCH();
     }
     h->cur ^= 1;
     h->n = n_sorted;
     return SPH_OK;
 }
 
-// Launch-shape variants of the density kernel (SPH_B200_DENSITY_CFG, experiments).
+// Density pass. Default: the pair walk (two rows per thread, packed fp32x2 tests, bitmask compaction;
+// sph_physics.cuh) followed by the rows it could not pair and by the heavy tail. SPH_B200_DENSITY_CFG >= 10
+// selects the round-1 one-row-per-thread kernel and its launch shapes (kept for A/B measurements: the two
+// produce bit-identical lists and densities).
 int launch_density(sph_handle *h, uint32_t n)
 {
+    cudaStream_t s = h->stream;
 #define LAUNCH_D(S, B, U)                                                                                  \
-    k_density<S, B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(                          \
+    k_density<S, B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                                  \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->ctr)
+#define LAUNCH_P(B)                                                                                        \
+    k_density_pair<B><<<blocks_for((n + 1) / 2, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                         \
+        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
+        h->order, h->single_list, h->ctr)
+    bool paired = true;
     switch (h->density_cfg) {
-    case 1: LAUNCH_D(24, 1, 4); break;
-    case 2: LAUNCH_D(24, 1, 2); break;
-    case 3: LAUNCH_D(24, 12, 4); break;
-    case 4: LAUNCH_D(24, 1, 3); break;
-    case 5: LAUNCH_D(24, 1, 1); break;
-    default: LAUNCH_D(24, 12, 2); break;  // 40 registers: best of the shapes tried at both 1 M (dense) and 8 M (sparse)
+    case 1: LAUNCH_P(6); break;
+    case 2: LAUNCH_P(10); break;
+    case 3: LAUNCH_P(12); break;
+    case 10: LAUNCH_D(24, 12, 2); paired = false; break;  // round-1 default
+    case 11: LAUNCH_D(24, 1, 4); paired = false; break;
+    case 12: LAUNCH_D(24, 1, 2); paired = false; break;
+    default: LAUNCH_P(8); break;
     }
 #undef LAUNCH_D
-    CK_LAUNCH();
+#undef LAUNCH_P
+    CK_STEP_LAUNCH();
+    if (paired) {
+        k_density_single<<<h->num_sms * 2, PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
+                                                                h->nlist, h->ncount, (uint32_t)h->cap, h->order,
+                                                                h->single_list, h->ctr);
+        CK_STEP_LAUNCH();
+    }
     // the heavy tail (clumps, hash-collision cells), one warp per deferred particle; exits at once when empty
-    k_density_heavy<<<h->num_sms * 4, HEAVY_THREADS, 0, h->stream>>>(h->pos[h->cur], h->gd, h->cells, h->P, h->vel[h->cur],
-                                                                    h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
-    CK_LAUNCH();
+    k_density_heavy<<<h->num_sms * 4, HEAVY_THREADS, 0, s>>>(h->pos[h->cur], h->gd, h->cells, h->P, h->vel[h->cur],
+                                                            h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
+    CK_STEP_LAUNCH();
     return SPH_OK;
 }
 
@@ -365,12 +386,12 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
         }
     }
 #undef LAUNCH_FI
-    CK_LAUNCH();
+    CK_STEP_LAUNCH();
     if (mode == FI_FORCE_ONLY) LAUNCH_FH(FI_FORCE_ONLY);
     else if (mode == FI_STEP_WRITE_FORCE) LAUNCH_FH(FI_STEP_WRITE_FORCE);
     else LAUNCH_FH(FI_STEP);
 #undef LAUNCH_FH
-    CK_LAUNCH();
+    CK_STEP_LAUNCH();
     if (mode != FI_FORCE_ONLY) {
         h->cur ^= 1;
         h->have_force = mode == FI_STEP_WRITE_FORCE;
@@ -413,7 +434,6 @@ int step_once(sph_handle *h, float dt)
     if (rc) return rc;
     if (timed) CK(cudaEventRecord(ev[3], s));
     if (timed) CK(cudaEventRecord(ev[4], s));
-    h->launches += 9;  // plan+zero, hist, scan, place, order+gather, density (+heavy), forces+integrate (+heavy)
     h->parity ^= 1;
     ++h->steps;
     h->have_step = true;
@@ -439,6 +459,7 @@ int capture_steps(sph_handle *h, float dt, int len, cudaGraphExec_t *out)
     for (int k = 0; k < len && !rc; ++k) rc = step_once(h, dt);
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+    h->graph_launches[len == 1 ? 0 : 1] = h->launches - launches;
     h->cur = cur; h->parity = parity; h->steps = steps; h->launches = launches;
     h->have_step = have_step; h->have_force = have_force;
     if (rc) {
@@ -473,7 +494,7 @@ int step_graphs(sph_handle *h, float dt, int nsteps)
         }
         CK(cudaGraphLaunch(ex, h->stream));
         h->steps += len;
-        h->launches += 9ull * len;
+        h->launches += h->graph_launches[li];
         if (len & 1) h->parity ^= 1;
         h->have_step = true;
         h->have_force = h->write_force;
@@ -633,6 +654,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaMalloc(&nh->slab_counts, sizeof(unsigned long long) * (2 * SLAB_MAX_RANKS + 8)));
     CKC(cudaMalloc(&nh->order, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->map, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->single_list, sizeof(uint32_t) * (cap / 2 + 16)));
     CKC(cudaMalloc(&nh->cells, sizeof(uint32_t) * ((size_t)nh->max_cells + 8)));
     CKC(cudaMalloc(&nh->h16_cells, sizeof(uint32_t) * 65540));
     CKC(cudaMalloc(&nh->const_65536, sizeof(uint32_t)));
@@ -663,7 +685,7 @@ int sph_destroy(sph_handle *h)
     for (int b = 0; b < 2; ++b) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); }
     cudaFree(h->force); cudaFree(h->hash16); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot); cudaFree(h->inverse);
     cudaFree(h->halo_rows[0]); cudaFree(h->halo_rows[1]); cudaFree(h->slab_counts);
-    cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
+    cudaFree(h->order); cudaFree(h->map); cudaFree(h->single_list); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
     cudaFree(h->stats_acc); cudaFree(h->scratch);
     for (int k = 0; k < 2; ++k)
@@ -890,7 +912,6 @@ int sph_neighbor_search(sph_handle *h, int repeats)
         // the box of the current positions is in bbox[parity]; the plan re-arms the other slot only
         rc = build_grid(h);
         if (rc) return rc;
-        h->launches += 5;
     }
     h->have_step = false;
     return SPH_OK;
@@ -1123,6 +1144,45 @@ int sph_selftest_division(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mi
     return SPH_OK;
 }
 
+int sph_selftest_pair_dist2(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out)
+{
+    int rc = enter(h);
+    if (rc) return rc;
+    if (!mismatches_out || n == 0 || n > (1ull << 26)) return fail(h, SPH_ERR_INVALID, "bad arguments");
+    // Positions as the candidate loops see them: two rows and a candidate a fraction of a cell apart,
+    // anywhere in the box (magnitudes up to 16), plus exact coincidences and far-apart triples.
+    std::vector<float> v(12 * n);
+    uint64_t x = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto next = [&]() { x = x * 6364136223846793005ull + 1442695040888963407ull; return (double)(x >> 11) / 9007199254740992.0; };
+    for (uint64_t i = 0; i < n; ++i) {
+        const double scale = std::pow(10.0, -3.0 + 3.0 * next());  // separation scale 1e-3 .. 1
+        float *a = &v[4 * i], *b = &v[4 * (n + i)], *c = &v[4 * (2 * n + i)];
+        for (int k = 0; k < 3; ++k) {
+            const double base = -16.0 + 32.0 * next();
+            a[k] = (float)base;
+            b[k] = (float)(base + scale * (next() - 0.5));
+            c[k] = (i % 97 == 0) ? a[k] : (float)(base + scale * (next() - 0.5));
+        }
+        a[3] = b[3] = c[3] = 0.f;
+    }
+    const size_t bytes = align_up(sizeof(float) * 4 * n, 256);
+    rc = ensure_scratch(h, 3 * bytes + 256);
+    if (rc) return rc;
+    char *sc = (char *)h->scratch;
+    uint32_t *dout = (uint32_t *)(sc + 3 * bytes);
+    for (int k = 0; k < 3; ++k)
+        CK(cudaMemcpyAsync(sc + k * bytes, v.data() + 4 * n * k, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(dout, 0, sizeof(uint32_t), h->stream));
+    k_selftest_pair_dist2<<<blocks_for(n, 256), 256, 0, h->stream>>>((const float4 *)sc, (const float4 *)(sc + bytes),
+                                                                    (const float4 *)(sc + 2 * bytes), (uint32_t)n, dout);
+    CK_LAUNCH();
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, dout, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *mismatches_out = bad;
+    return SPH_OK;
+}
+
 // ---- slab decomposition ---------------------------------------------------------------------------
 
 namespace {
@@ -1269,7 +1329,6 @@ int sph_slab_step_density(sph_handle *h)
         rc = launch_density(h, n);
         if (rc) return rc;
     }
-    h->launches += 7;
     return SPH_OK;
 }
 
@@ -1317,7 +1376,6 @@ int sph_slab_step_forces(sph_handle *h, float dt)
         h->parity ^= 1;  // the integration accumulated the next step's box into the other slot
         h->have_bbox_from_integration = true;
     }
-    h->launches += 2;
     ++h->steps;
     h->have_step = true;
     h->edge_ok = true;

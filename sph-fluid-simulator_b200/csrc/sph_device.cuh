@@ -52,6 +52,7 @@ struct StepCounters {
     uint32_t heavy[2];    // particles deferred to the warp-cooperative density / force kernels
     uint32_t epoch;       // tag of the current scan's tile states; bumped on the device so a captured step replays
     uint32_t fast_x;      // some particle moved half a cell or more along x in the last integration (slab edge scans)
+    uint32_t single;      // rows the pair-walk density kernel could not pair with their neighbour row (walked alone afterwards)
 };
 
 // Settings + derived constants, passed to kernels by value.
@@ -134,6 +135,47 @@ __device__ __forceinline__ uint32_t grid_index(const GridDesc &g, int cx, int cy
 __device__ __forceinline__ float dist2_rn(float dx, float dy, float dz)
 {
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---- packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2) ------------------------------
+// Two IEEE round-to-nearest fp32 operations per instruction on a 64-bit register pair. Each half
+// is rounded exactly like the scalar __fadd_rn / __fmul_rn / __fmaf_rn, so results are
+// bit-identical to the scalar forms; the point is half the issue slots in the neighbour loops.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b)
+{
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c)
+{
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
 }
 
 // ---- small warp helpers -------------------------------------------------------------------

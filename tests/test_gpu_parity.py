@@ -219,6 +219,14 @@ def test_shared_reciprocal_division_is_ieee(sph):
     sim.close()
 
 
+def test_packed_pair_dist2_is_the_scalar_dist2(sph):
+    """FADD2 / FMUL2 halves of the density pass's candidate test against the unfused scalar expression
+    (guards against the toolchain contracting packed mul + add into FFMA2)."""
+    sim = sph.Sim(sph.default_settings(), capacity=1024)
+    assert sim.selftest_pair_dist2(1 << 22, seed=3) == 0
+    sim.close()
+
+
 def test_long_run_statistics(sph, oracle):
     """Chaotic beyond ~50 steps: compare statistics only (App. B: mean density within 2 %, KE 1 %)."""
     s = sph.default_settings()
