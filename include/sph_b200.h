@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SPH_B200_ABI_VERSION 1
+#define SPH_B200_ABI_VERSION 2
 
 enum sph_status {
     SPH_OK = 0,
@@ -80,6 +80,7 @@ typedef struct sph_stats {
     uint64_t deferred_density; /* particles the last step handed to the warp-cooperative density kernel */
     uint64_t deferred_forces;  /* ... and to the warp-cooperative force kernel */
     uint64_t nlist_rows;       /* rows of the per-particle neighbour list; particles with more neighbours are deferred */
+    uint64_t unpaired_rows;    /* rows the pair-walk density kernel walked alone in the last step (no neighbour row to share a walk with) */
 } sph_stats;
 
 typedef struct sph_handle sph_handle;

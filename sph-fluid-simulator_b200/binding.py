@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("grid_dim", C.c_int32 * 3), ("grid_cells", C.c_uint64), ("clamped", C.c_uint64),
                 ("nan_count", C.c_uint64), ("mean_density", C.c_double), ("max_density", C.c_double),
                 ("kinetic_energy", C.c_double), ("deferred_density", C.c_uint64), ("deferred_forces", C.c_uint64),
-                ("nlist_rows", C.c_uint64)]
+                ("nlist_rows", C.c_uint64), ("unpaired_rows", C.c_uint64)]
 
 
 _lib = None

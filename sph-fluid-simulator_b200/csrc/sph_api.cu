@@ -312,25 +312,58 @@ int launch_density(sph_handle *h, uint32_t n)
     k_density<S, B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                                  \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->ctr)
-#define LAUNCH_P(B)                                                                                        \
-    k_density_pair<B><<<blocks_for((n + 1) / 2, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                         \
+#define LAUNCH_P(B, U)                                                                                     \
+    k_density_pair<B, U><<<blocks_for((n + 1) / 2, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                         \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->single_list, h->ctr)
+#define LAUNCH_R(B, U)                                                                                     \
+    k_density_row<B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                                 \
+        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
+        h->order, h->ctr)
+#define LAUNCH_S(B, U)                                                                                     \
+    k_density_staged<B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                              \
+        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
+        h->order, h->ctr)
+#define LAUNCH_PS(B, U)                                                                                    \
+    k_density_pair_staged<B, U><<<blocks_for((n + 1) / 2, PHYS_THREADS), PHYS_THREADS, 0, s>>>(               \
+        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
+        h->order, h->ctr)
     bool paired = true;
-    switch (h->density_cfg) {
-    case 1: LAUNCH_P(6); break;
-    case 2: LAUNCH_P(10); break;
-    case 3: LAUNCH_P(12); break;
+    int cfg = h->density_cfg;
+    if (cfg != 10 && cfg != 11 && cfg != 12 && (uint64_t)(NLIST_ROWS + HEAVY_RUN + 1) * h->cap >= (1ull << 32)) cfg = 10;  // the newer kernels keep 32-bit list offsets
+    switch (cfg) {
+    case 1: LAUNCH_P(8, 2); break;
+    case 2: LAUNCH_P(10, 4); break;
+    case 3: LAUNCH_P(10, 2); break;
+    case 4: LAUNCH_P(12, 2); break;
+    case 5: LAUNCH_P(8, 1); break;
+    case 40: LAUNCH_PS(8, 2); paired = false; break;
+    case 41: LAUNCH_PS(8, 4); paired = false; break;
+    case 42: LAUNCH_PS(10, 2); paired = false; break;
+    case 43: LAUNCH_PS(8, 1); paired = false; break;
+    case 44: LAUNCH_PS(6, 2); paired = false; break;
+    case 30: LAUNCH_S(12, 2); paired = false; break;
+    case 31: LAUNCH_S(12, 4); paired = false; break;
+    case 32: LAUNCH_S(10, 2); paired = false; break;
+    case 33: LAUNCH_S(16, 2); paired = false; break;
+    case 20: LAUNCH_R(12, 2); paired = false; break;
+    case 21: LAUNCH_R(12, 4); paired = false; break;
+    case 22: LAUNCH_R(16, 2); paired = false; break;
+    case 23: LAUNCH_R(8, 4); paired = false; break;
+    case 24: LAUNCH_R(12, 1); paired = false; break;
     case 10: LAUNCH_D(24, 12, 2); paired = false; break;  // round-1 default
     case 11: LAUNCH_D(24, 1, 4); paired = false; break;
     case 12: LAUNCH_D(24, 1, 2); paired = false; break;
-    default: LAUNCH_P(8); break;
+    default: LAUNCH_P(8, 4); break;
     }
 #undef LAUNCH_D
 #undef LAUNCH_P
+#undef LAUNCH_R
+#undef LAUNCH_S
+#undef LAUNCH_PS
     CK_STEP_LAUNCH();
     if (paired) {
-        k_density_single<<<h->num_sms * 2, PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
+        k_density_single<<<h->num_sms * 8, PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
                                                                 h->nlist, h->ncount, (uint32_t)h->cap, h->order,
                                                                 h->single_list, h->ctr);
         CK_STEP_LAUNCH();
@@ -1072,6 +1105,7 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     out->deferred_density = c.heavy[0];
     out->deferred_forces = c.heavy[1];
     out->nlist_rows = NLIST_ROWS;
+    out->unpaired_rows = c.single;
     out->nan_count = a.nan_count;
     if (h->have_step) out->count = a.owned;
     out->mean_density = a.sum_rho / (double)(a.owned ? a.owned : 1);
