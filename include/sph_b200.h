@@ -80,7 +80,6 @@ typedef struct sph_stats {
     uint64_t deferred_density; /* particles the last step handed to the warp-cooperative density kernel */
     uint64_t deferred_forces;  /* ... and to the warp-cooperative force kernel */
     uint64_t nlist_rows;       /* rows of the per-particle neighbour list; particles with more neighbours are deferred */
-    uint64_t unpaired_rows;    /* rows the pair-walk density kernel walked alone in the last step (no neighbour row to share a walk with) */
 } sph_stats;
 
 typedef struct sph_handle sph_handle;
@@ -197,10 +196,10 @@ uint64_t sph_launch_count(const sph_handle *h);
  * n pseudo-random pairs and returns the number of mismatches (expected 0). */
 int sph_selftest_division(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out);
 
-/* Device self-test: the density pass tests one candidate against two rows with packed fp32x2
- * arithmetic (csrc/sph_physics.cuh, pair_dist2); this checks both halves bit-for-bit against the scalar
- * (dx*dx + dy*dy) + dz*dz of glm::length2 (src/sph.cpp:57) on n pseudo-random triples (expected 0). */
-int sph_selftest_pair_dist2(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out);
+/* Device self-test: the density pass forms dx, dy and their squares with packed fp32x2 arithmetic
+ * (csrc/sph_physics.cuh, row_dist2); this checks it bit-for-bit against the scalar
+ * (dx*dx + dy*dy) + dz*dz of glm::length2 (src/sph.cpp:57) on 2n pseudo-random pairs (expected 0). */
+int sph_selftest_packed_dist2(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out);
 
 /* Raw CUDA stream of the handle (cudaStream_t as void*), so a caller can order its own work or
  * record events on it. */

@@ -49,7 +49,7 @@ class Stats(C.Structure):
                 ("grid_dim", C.c_int32 * 3), ("grid_cells", C.c_uint64), ("clamped", C.c_uint64),
                 ("nan_count", C.c_uint64), ("mean_density", C.c_double), ("max_density", C.c_double),
                 ("kinetic_energy", C.c_double), ("deferred_density", C.c_uint64), ("deferred_forces", C.c_uint64),
-                ("nlist_rows", C.c_uint64), ("unpaired_rows", C.c_uint64)]
+                ("nlist_rows", C.c_uint64)]
 
 
 _lib = None
@@ -98,7 +98,7 @@ def load_library() -> C.CDLL:
         "sph_pass_times": ([hp, fp, u64p], C.c_int),
         "sph_launch_count": ([hp], C.c_uint64),
         "sph_selftest_division": ([hp, C.c_uint64, C.c_uint64, u64p], C.c_int),
-        "sph_selftest_pair_dist2": ([hp, C.c_uint64, C.c_uint64, u64p], C.c_int),
+        "sph_selftest_packed_dist2": ([hp, C.c_uint64, C.c_uint64, u64p], C.c_int),
         "sph_stream": ([hp], C.c_void_p),
         "sph_scene_cube": ([C.c_int, C.c_float, fp, fp], C.c_int),
         "sph_scene_block": ([C.c_int] * 3 + [C.c_float] * 5 + [C.c_uint, fp, fp], C.c_int),
@@ -354,9 +354,9 @@ class Sim:
         self._ck(self.lib.sph_selftest_division(self._h, n, seed, C.byref(bad)))
         return int(bad.value)
 
-    def selftest_pair_dist2(self, n=1 << 22, seed=1) -> int:
+    def selftest_packed_dist2(self, n=1 << 22, seed=1) -> int:
         bad = C.c_uint64(0)
-        self._ck(self.lib.sph_selftest_pair_dist2(self._h, n, seed, C.byref(bad)))
+        self._ck(self.lib.sph_selftest_packed_dist2(self._h, n, seed, C.byref(bad)))
         return int(bad.value)
 
     @property

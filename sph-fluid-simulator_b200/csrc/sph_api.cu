@@ -50,7 +50,6 @@ struct sph_handle {
     uint32_t *nlist = nullptr, *ncount = nullptr;  // neighbour lists written by the density pass
     uint2 *cell_rank = nullptr, *slot = nullptr;
     uint32_t *order = nullptr, *map = nullptr;
-    uint32_t *single_list = nullptr;      // rows the pair-walk density kernel left for k_density_single
     uint32_t *inverse = nullptr;          // sorted row of each pre-sort row (slab mode)
     uint32_t *halo_rows[2] = {nullptr, nullptr};  // pre-sort rows packed into each halo message
     uint64_t halo_n[2] = {0, 0};
@@ -301,10 +300,10 @@ int build_grid(sph_handle *h)
     return SPH_OK;
 }
 
-// Density pass. Default: the pair walk (two rows per thread, packed fp32x2 tests, bitmask compaction;
-// sph_physics.cuh) followed by the rows it could not pair and by the heavy tail. SPH_B200_DENSITY_CFG >= 10
-// selects the round-1 one-row-per-thread kernel and its launch shapes (kept for A/B measurements: the two
-// produce bit-identical lists and densities).
+// Density pass. Default: the staged row walk (sph_physics.cuh); SPH_B200_DENSITY_CFG >= 10 selects the
+// round-1 kernel and its launch shapes, 1..3 other launch shapes of the staged walk (A/B measurements:
+// all variants produce bit-identical lists and densities). The staged walk keeps 32-bit list offsets;
+// capacities beyond that take the round-1 kernel.
 int launch_density(sph_handle *h, uint32_t n)
 {
     cudaStream_t s = h->stream;
@@ -312,62 +311,24 @@ int launch_density(sph_handle *h, uint32_t n)
     k_density<S, B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                                  \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->ctr)
-#define LAUNCH_P(B, U)                                                                                     \
-    k_density_pair<B, U><<<blocks_for((n + 1) / 2, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                         \
-        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
-        h->order, h->single_list, h->ctr)
-#define LAUNCH_R(B, U)                                                                                     \
-    k_density_row<B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                                 \
-        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
-        h->order, h->ctr)
 #define LAUNCH_S(B, U)                                                                                     \
     k_density_staged<B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                              \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->ctr)
-#define LAUNCH_PS(B, U)                                                                                    \
-    k_density_pair_staged<B, U><<<blocks_for((n + 1) / 2, PHYS_THREADS), PHYS_THREADS, 0, s>>>(               \
-        h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
-        h->order, h->ctr)
-    bool paired = true;
     int cfg = h->density_cfg;
-    if (cfg != 10 && cfg != 11 && cfg != 12 && (uint64_t)(NLIST_ROWS + HEAVY_RUN + 1) * h->cap >= (1ull << 32)) cfg = 10;  // the newer kernels keep 32-bit list offsets
+    if (cfg < 10 && (uint64_t)(NLIST_ROWS + 1) * h->cap >= (1ull << 32)) cfg = 10;
     switch (cfg) {
-    case 1: LAUNCH_P(8, 2); break;
-    case 2: LAUNCH_P(10, 4); break;
-    case 3: LAUNCH_P(10, 2); break;
-    case 4: LAUNCH_P(12, 2); break;
-    case 5: LAUNCH_P(8, 1); break;
-    case 40: LAUNCH_PS(8, 2); paired = false; break;
-    case 41: LAUNCH_PS(8, 4); paired = false; break;
-    case 42: LAUNCH_PS(10, 2); paired = false; break;
-    case 43: LAUNCH_PS(8, 1); paired = false; break;
-    case 44: LAUNCH_PS(6, 2); paired = false; break;
-    case 30: LAUNCH_S(12, 2); paired = false; break;
-    case 31: LAUNCH_S(12, 4); paired = false; break;
-    case 32: LAUNCH_S(10, 2); paired = false; break;
-    case 33: LAUNCH_S(16, 2); paired = false; break;
-    case 20: LAUNCH_R(12, 2); paired = false; break;
-    case 21: LAUNCH_R(12, 4); paired = false; break;
-    case 22: LAUNCH_R(16, 2); paired = false; break;
-    case 23: LAUNCH_R(8, 4); paired = false; break;
-    case 24: LAUNCH_R(12, 1); paired = false; break;
-    case 10: LAUNCH_D(24, 12, 2); paired = false; break;  // round-1 default
-    case 11: LAUNCH_D(24, 1, 4); paired = false; break;
-    case 12: LAUNCH_D(24, 1, 2); paired = false; break;
-    default: LAUNCH_P(8, 4); break;
+    case 1: LAUNCH_S(12, 4); break;
+    case 2: LAUNCH_S(10, 2); break;
+    case 3: LAUNCH_S(16, 2); break;
+    case 10: LAUNCH_D(24, 12, 2); break;  // round-1 default
+    case 11: LAUNCH_D(24, 1, 4); break;
+    case 12: LAUNCH_D(24, 1, 2); break;
+    default: LAUNCH_S(12, 2); break;  // 40 registers, 12.8 KB of shared memory: best at 1 M (dense); cfg 3 wins by 5 % at 8 M (sparse)
     }
 #undef LAUNCH_D
-#undef LAUNCH_P
-#undef LAUNCH_R
 #undef LAUNCH_S
-#undef LAUNCH_PS
     CK_STEP_LAUNCH();
-    if (paired) {
-        k_density_single<<<h->num_sms * 8, PHYS_THREADS, 0, s>>>(h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
-                                                                h->nlist, h->ncount, (uint32_t)h->cap, h->order,
-                                                                h->single_list, h->ctr);
-        CK_STEP_LAUNCH();
-    }
     // the heavy tail (clumps, hash-collision cells), one warp per deferred particle; exits at once when empty
     k_density_heavy<<<h->num_sms * 4, HEAVY_THREADS, 0, s>>>(h->pos[h->cur], h->gd, h->cells, h->P, h->vel[h->cur],
                                                             h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
@@ -687,7 +648,6 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaMalloc(&nh->slab_counts, sizeof(unsigned long long) * (2 * SLAB_MAX_RANKS + 8)));
     CKC(cudaMalloc(&nh->order, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->map, sizeof(uint32_t) * cap));
-    CKC(cudaMalloc(&nh->single_list, sizeof(uint32_t) * (cap / 2 + 16)));
     CKC(cudaMalloc(&nh->cells, sizeof(uint32_t) * ((size_t)nh->max_cells + 8)));
     CKC(cudaMalloc(&nh->h16_cells, sizeof(uint32_t) * 65540));
     CKC(cudaMalloc(&nh->const_65536, sizeof(uint32_t)));
@@ -718,7 +678,7 @@ int sph_destroy(sph_handle *h)
     for (int b = 0; b < 2; ++b) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); }
     cudaFree(h->force); cudaFree(h->hash16); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot); cudaFree(h->inverse);
     cudaFree(h->halo_rows[0]); cudaFree(h->halo_rows[1]); cudaFree(h->slab_counts);
-    cudaFree(h->order); cudaFree(h->map); cudaFree(h->single_list); cudaFree(h->cells); cudaFree(h->h16_cells);
+    cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
     cudaFree(h->stats_acc); cudaFree(h->scratch);
     for (int k = 0; k < 2; ++k)
@@ -1105,7 +1065,6 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     out->deferred_density = c.heavy[0];
     out->deferred_forces = c.heavy[1];
     out->nlist_rows = NLIST_ROWS;
-    out->unpaired_rows = c.single;
     out->nan_count = a.nan_count;
     if (h->have_step) out->count = a.owned;
     out->mean_density = a.sum_rho / (double)(a.owned ? a.owned : 1);
@@ -1178,7 +1137,7 @@ int sph_selftest_division(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mi
     return SPH_OK;
 }
 
-int sph_selftest_pair_dist2(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out)
+int sph_selftest_packed_dist2(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *mismatches_out)
 {
     int rc = enter(h);
     if (rc) return rc;
@@ -1207,7 +1166,7 @@ int sph_selftest_pair_dist2(sph_handle *h, uint64_t n, uint64_t seed, uint64_t *
     for (int k = 0; k < 3; ++k)
         CK(cudaMemcpyAsync(sc + k * bytes, v.data() + 4 * n * k, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemsetAsync(dout, 0, sizeof(uint32_t), h->stream));
-    k_selftest_pair_dist2<<<blocks_for(n, 256), 256, 0, h->stream>>>((const float4 *)sc, (const float4 *)(sc + bytes),
+    k_selftest_packed_dist2<<<blocks_for(n, 256), 256, 0, h->stream>>>((const float4 *)sc, (const float4 *)(sc + bytes),
                                                                     (const float4 *)(sc + 2 * bytes), (uint32_t)n, dout);
     CK_LAUNCH();
     uint32_t bad = 0;

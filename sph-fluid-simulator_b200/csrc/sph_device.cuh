@@ -52,7 +52,6 @@ struct StepCounters {
     uint32_t heavy[2];    // particles deferred to the warp-cooperative density / force kernels
     uint32_t epoch;       // tag of the current scan's tile states; bumped on the device so a captured step replays
     uint32_t fast_x;      // some particle moved half a cell or more along x in the last integration (slab edge scans)
-    uint32_t single;      // rows the pair-walk density kernel could not pair with their neighbour row (walked alone afterwards)
 };
 
 // Settings + derived constants, passed to kernels by value.

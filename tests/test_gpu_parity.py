@@ -219,11 +219,11 @@ def test_shared_reciprocal_division_is_ieee(sph):
     sim.close()
 
 
-def test_packed_pair_dist2_is_the_scalar_dist2(sph):
-    """FADD2 / FMUL2 halves of the density pass's candidate test against the unfused scalar expression
+def test_packed_dist2_is_the_scalar_dist2(sph):
+    """The FADD2 / FMUL2 form of the density pass's candidate test against the unfused scalar expression
     (guards against the toolchain contracting packed mul + add into FFMA2)."""
     sim = sph.Sim(sph.default_settings(), capacity=1024)
-    assert sim.selftest_pair_dist2(1 << 22, seed=3) == 0
+    assert sim.selftest_packed_dist2(1 << 22, seed=3) == 0
     sim.close()
 
 

@@ -57,6 +57,6 @@ for name, h, (nx, ny, nz) in scenes:
             print(json.dumps({"scene": name, "n": n, "density_cfg": cfg, "forces_cfg": fcfg,
                               "pass_ms": {k: round(v, 4) for k, v in pt.items() if k != "steps"},
                               "step_ms": round(sum(v for k, v in pt.items() if k != "steps"), 4),
-                              "bits_equal_to_first": same, "deferred_density": int(st.deferred_density), "unpaired_rows": int(st.unpaired_rows),
+                              "bits_equal_to_first": same, "deferred_density": int(st.deferred_density),
                               "mean_density": round(st.mean_density, 4)}), flush=True)
             sim.close()
