@@ -16,7 +16,14 @@ Timing: CUDA events on the library's stream around each step, L2 flushed (256 Mi
 timed steps, max over ranks. `value` has the state resident in HBM; `e2e` goes through the
 stateless drop-in call (sph_update_particles_aos: 60-byte Particle rows in pinned host memory up,
 Particle rows + mat4 transforms down, every step). `--impl reference` times the reference's own
-CPU step (oracle/_ref, or the oracle port when that is not built) on the host cores.
+CPU step (oracle/_ref, or the oracle port when that is not built) on the host cores; that arm
+imports nothing of the product (the scene comes from the oracle's generator, which the tests prove
+bit-identical to the product's).
+
+Scaling series: the N = 1 line is config 1 (the configuration the metric is quoted on); the like-for-like
+single-GPU point of the weak-scaling series (config 3, one 8 M block) is measured in the same N = 1 run and
+carried as config.weak_scaling_base, and every N > 1 line carries the same measurement taken in its own job
+(config.single_gpu_same_workload) together with config.scaling_efficiency_vs_same_workload.
 """
 import argparse
 import json
@@ -67,14 +74,37 @@ def dam_break_16m(g):
     return dict(name="dam-break-16M", h=h, sep=sep, dims=(nx, ny, nz), origin=origin, seed=1024, scaling="strong")
 
 
+def scaled_settings7(h):
+    """SURVEY.md 8(d) scaling of the shipped defaults, as sph_b200.scaled_settings computes it (float32
+    arithmetic), without importing the product: (mass, restDensity, gasConstant, viscosity, h, g, tension), dt."""
+    k = np.float32(h) / np.float32(0.15)
+    mass = float(np.float32(0.02) * k * k * k)
+    dt = float(np.float32(0.003) * k)
+    return (mass, 1000.0, 1.0, 1.04, float(np.float32(h)), -9.8, 0.2), dt
+
+
+def source_hash():
+    """Hash of the CUDA sources: a committed ncu traffic figure is only quoted for the code it was taken on."""
+    import hashlib
+    hsh = hashlib.sha256()
+    d = os.path.join(ROOT, "sph-fluid-simulator_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            hsh.update(fh.read())
+    return hsh.hexdigest()[:16]
+
+
 def measured_traffic(kernel):
     """DRAM bytes per launch of a kernel from the committed ncu --set full capture of this workload
     (profiles/r01_traffic.json, written by tools/ncu_traffic.py), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
-        return json.load(f).get(kernel)
+        t = json.load(f)
+    if t.get("source_hash") != source_hash():
+        return None  # captured on other kernels: stale, not quoted
+    return t.get("kernels", {}).get(kernel)
 
 
 def peaks():
@@ -86,9 +116,13 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled during the timed region: NVML from a thread every 100 ms
-    (a sample costs microseconds, so even a quarter-second region gets several), nvidia-smi -lms as the
-    fallback when the NVML binding is missing."""
+    """SM clock and throttle reasons for the timed region. An NVML query is NOT free for the GPU it asks about:
+    measured in round 2 on a two-GPU run, every query stalls that rank's kernel launches for ~10 ms (polling
+    every 100 ms cost the sampled rank 0.9 ms per step of a 20-step region, every 20 ms from a separate
+    process 5 ms per step). So: one sample when the region starts (before the first timed launch), one the
+    moment it ends (the GPU is still at its load clocks), and in between only one every 0.5 s — a long region
+    is sampled throughout, a 25 ms one is not disturbed. nvidia-smi -lms as the fallback without the NVML binding."""
+    PERIOD_S = 0.5
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -132,18 +166,18 @@ class ClockSampler:
             pass
 
     def _loop(self):
-        while not self._stop.is_set():
+        while not self._stop.wait(self.PERIOD_S):
             self._sample()
-            self._stop.wait(0.1)
 
     def start(self):
         if self.nvml:
+            self._sample()  # region start (the launches that follow are not timed yet: events bracket the region)
             self._thread = threading.Thread(target=self._loop, daemon=True)
             self._thread.start()
             return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "500"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -164,7 +198,8 @@ class ClockSampler:
             for _, b in self.samples:
                 bits |= b
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
-                    "reasons": sorted(k for k, v in self.BITS.items() if bits & v), "samples": len(sm), "source": "nvml"}
+                    "reasons": sorted(k for k, v in self.BITS.items() if bits & v), "samples": len(sm),
+                    "source": f"nvml: at the start and the end of the timed region and every {self.PERIOD_S} s in between"}
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -195,41 +230,48 @@ def reference_step_fn():
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_sample(scene, time_steps, settle, warmup, steps, budget_s):
+    """The reference CPU step on a bounded sample of `scene`: a z-slice of the same lattice (the fluid spans
+    the full z width; the x-y cross section is kept), sized so that settle + warm-up + timed steps fit the
+    budget; the rate is probed on a thin slice first. Nothing of the product is imported: the lattice comes
+    from the oracle's generator (bit-identical to the product's, tests/test_abi.py)."""
+    from oracle.pyoracle import Oracle
+    O = Oracle()
+    s7, dt = scaled_settings7(scene["h"])
+    nx, ny, nz = scene["dims"]
+    pos, vel = O.init_block(nx, ny, 8, scene["sep"], scene["origin"], scene["h"], scene["seed"])
+    sec, _, _ = time_steps(s7, dt, 1, 2, pos, vel)
+    rate = pos.shape[0] * 2 / sec
+    total_steps = settle + warmup + steps
+    n_budget = rate * budget_s / max(total_steps, 1)
+    snz = int(max(4, min(nz, n_budget // (nx * ny))))
+    origin = (scene["origin"][0], scene["origin"][1], -snz * scene["sep"] / 2.0)
+    pos, vel = O.init_block(nx, ny, snz, scene["sep"], origin, scene["h"], scene["seed"])
+    n = pos.shape[0]
+    _, pos, vel = time_steps(s7, dt, settle, 0, pos, vel)
+    sec, pos, vel = time_steps(s7, dt, warmup, steps, pos, vel)
+    sample = (f"{nx}x{ny}x{snz} = {n} particle slice of the {scene['name']} lattice ({nx * ny * nz} particles), "
+              f"settled {settle} steps on the CPU, then {steps} timed steps ({sec:.1f} s)")
+    return n, sec, dt, sample
+
+
 def run_reference(args):
     """The reference's own CPU step on the host cores, same metric. Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    import sph_b200 as S
     kind, cores, time_steps = reference_step_fn()
     scene = dam_break_1m() if args.gpus == 1 else weak_scaling_block(args.gpus)
-    s = S.scaled_settings(scene["h"])
-    s7 = s.as_tuple7()
     nx, ny, nz = scene["dims"]
-    # Bounded sample: a z-slice of the same lattice (the fluid spans the full z width; the x-y cross
-    # section is kept), sized so that settle + warm-up + timed steps fit the budget. The rate is
-    # probed on a thin slice first.
-    pos, vel = S.scene_block(nx, ny, 8, scene["sep"], scene["origin"], scene["h"], scene["seed"])
-    sec, _, _ = time_steps(s7, s.dt, 1, 2, pos, vel)
-    rate = pos.shape[0] * 2 / sec
-    total_steps = args.settle_reference + args.warmup + args.steps
-    n_budget = rate * args.reference_budget_s / max(total_steps, 1)
-    n_full = nx * ny * nz
-    snx = nx
-    snz = int(max(4, min(nz, n_budget // (nx * ny))))
-    origin = (scene["origin"][0], scene["origin"][1], -snz * scene["sep"] / 2.0)
-    pos, vel = S.scene_block(snx, ny, snz, scene["sep"], origin, scene["h"], scene["seed"])
-    n = pos.shape[0]
-    _, pos, vel = time_steps(s7, s.dt, args.settle_reference, 0, pos, vel)
-    sec, pos, vel = time_steps(s7, s.dt, args.warmup, args.steps, pos, vel)
+    n, sec, dt, sample = reference_sample(scene, time_steps, args.settle, args.warmup, args.steps, args.reference_budget_s)
     value = n * args.steps / sec
-    sample = (f"{snx}x{ny}x{snz} = {n} particle slice of the {scene['name']} lattice ({n_full} particles), "
-              f"settled {args.settle_reference} steps on the CPU, then {args.steps} timed steps")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": scene["name"], "particles_per_step": n, "h": scene["h"], "dt": s.dt,
-                   "note": "reference updateParticlesCPU on host threads; bounded sample, see cpu_baseline.sample"},
+        "config": {"workload": scene["name"], "particles": nx * ny * nz, "h": scene["h"], "dt": dt, "lattice": [nx, ny, nz],
+                   "settle_steps": args.settle, "sample_particles": n,
+                   "note": "reference updateParticlesCPU on host threads; a particle-step costs the same whatever the slice "
+                           "(the per-particle work is set by the local density, which the slice keeps), see cpu_baseline.sample"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -238,6 +280,17 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # 74.4: 148 SMs x 128 fp32 lanes x 2 (FMA) x 1.965 GHz
+
+
+def work_model(candidates_mean, neighbours_mean):
+    """SURVEY.md 8(d) FP32 work model, flop per particle-step: 9 per candidate pair in each of the two
+    neighbour passes, +6 per accepted neighbour in the density pass, +45 in the force pass."""
+    return {"density": 9.0 * candidates_mean + 6.0 * neighbours_mean,
+            "forces": 9.0 * candidates_mean + 45.0 * neighbours_mean,
+            "step": 18.0 * candidates_mean + 51.0 * neighbours_mean}
+
+
 def run_single_gpu(args):
     import torch
     import sph_b200 as S
@@ -257,15 +310,16 @@ def run_single_gpu(args):
     sim.step(args.settle)  # the lattice starts with zero neighbours (sep > h): let it collapse first
     sim.sync()
     settled = sim.download(S.ORDER_ID, fields=("pos", "vel"))
-    st0 = sim.stats()
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         sim.step(1)
     sim.sync()
 
+    # ---- the timed region: K steps through sph_step (the call a resident simulation makes: one captured
+    # CUDA graph per step), one event pair per step on the library's stream, L2 flushed between steps ----
     clocks = ClockSampler(dev)
     clocks.start()
-    sim.enable_pass_timing(True)
     launches0 = sim.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize(dev)
@@ -278,13 +332,21 @@ def run_single_gpu(args):
     sim.sync()
     torch.cuda.synchronize(dev)
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    passes = sim.pass_times()
-    sim.enable_pass_timing(False)
     launches = sim.launch_count - launches0
     clk = clocks.stop()
     total_s = float(step_ms.sum()) * 1e-3
     value = n * args.steps / total_s
     st1 = sim.stats()
+
+    # Per-pass shares from a separate short loop with per-pass events (host launches instead of the graph
+    # replay, L2 flushed the same way): the passes' SHARES apply to the timed steps, their sum is a little larger.
+    sim.enable_pass_timing(True)
+    with torch.cuda.stream(stream):
+        for _ in range(min(args.steps, 20)):
+            flush.zero_()
+            sim.step(1)
+    passes = sim.pass_times()
+    sim.enable_pass_timing(False)
 
     # Unflushed steady state (state stays in the 126 MB L2 between steps), for information.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,8 +357,10 @@ def run_single_gpu(args):
     sim.sync()
     warm_value = n * args.steps / (e0.elapsed_time(e1) * 1e-3)
 
-    # Neighbour statistics of the timed state (mean / max accepted neighbours).
+    # Work statistics of the timed state: candidates looked at and neighbours accepted per particle.
+    cand_mean = sim.candidates_mean()
     _, counts, _, _ = sim.neighbor_lists()
+    nb_mean = float(counts.mean())
 
     # ---- end to end through the stateless drop-in call, host buffers, copies inside the timing ----
     rows_t = torch.zeros((n, 15), dtype=torch.int32).pin_memory()
@@ -330,18 +394,50 @@ def run_single_gpu(args):
         assert rc == 0, lib.sph_last_error(sim.handle)
     e2e_s = time.perf_counter() - t0
     e2e_value = n * e2e_steps / e2e_s
+    sim.close()
 
-    # ---- roofline of the dominant kernel (live CUDA-event pass times over the timed region) ----
+    # ---- roofline of the dominant kernel: both roofs, from live CUDA-event pass times ----
     peak, peak_src = peaks()
-    pass_bytes = {"grid": B_ALG_GRID, "density": B_ALG_DENSITY, "forces": B_ALG_FORCES, "integrate": B_ALG_INTEGRATE}
+    flop = work_model(cand_mean, nb_mean)
+    pass_bytes = {"grid": B_ALG_GRID, "density": B_ALG_DENSITY, "forces": B_ALG_FORCES}
     dominant = max(("grid", "density", "forces"), key=lambda k: passes[k])
-    dom_name = {"forces": "k_forces_integrate", "density": "k_density", "grid": "grid build (5 kernels)", "integrate": "-"}[dominant]
-    achieved = pass_bytes[dominant] * n / (passes[dominant] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": measured_traffic(dom_name), "peak_source": peak_src,
+    dom_name = {"forces": "k_forces_integrate", "density": "k_density_staged", "grid": "grid build (5 kernels)"}[dominant]
+    per_pass = {}
+    for k in ("grid", "density", "forces"):
+        t = passes[k] * 1e-3
+        hbm = pass_bytes[k] * n / t / 1e9
+        row = {"ms": passes[k], "hbm_achieved_gbs": hbm, "hbm_frac": hbm / peak}
+        if k in flop:
+            row["fp32_achieved_tflops"] = flop[k] * n / t / 1e12
+            row["fp32_frac"] = row["fp32_achieved_tflops"] / FP32_PEAK_TFLOPS
+        row["bound"] = "hbm" if row["hbm_frac"] >= row.get("fp32_frac", 0.0) else "fp32-issue"
+        per_pass[k] = row
+    dom = per_pass[dominant]
+    if dom["bound"] == "hbm":
+        achieved, unit, rpeak = dom["hbm_achieved_gbs"], "GB/s", peak
+    else:
+        achieved, unit, rpeak = dom["fp32_achieved_tflops"], "TFLOP/s", FP32_PEAK_TFLOPS
+    roofline = {"bound": dom["bound"], "kernel": dom_name, "achieved": achieved, "peak": rpeak, "unit": unit,
+                "frac": achieved / rpeak, "traffic": measured_traffic(dom_name),
+                "peak_source": peak_src if dom["bound"] == "hbm" else
+                "148 SMs x 128 fp32 lanes x 2 (FMA) x 1.965 GHz; the step's arithmetic is unfused by contract, so 0.5 is its ceiling",
                 "algorithmic_bytes_per_launch": pass_bytes[dominant] * n,
-                "launch_ms": passes[dominant], "pass_ms": {k: passes[k] for k in pass_bytes},
-                "step_achieved_gbs": B_ALG_STEP * value / 1e9, "step_frac": B_ALG_STEP * value / 1e9 / peak}
+                "model_flop_per_launch": flop.get(dominant, 0.0) * n,
+                "launch_ms": passes[dominant], "per_pass": per_pass,
+                "work_model": "SURVEY.md 8(d): 9 flop per candidate pair and pass, +6 (density) / +45 (forces) per accepted "
+                              "neighbour; candidates_mean and neighbours_mean are in config",
+                "issue_note": "ncu (profiles/): the neighbour passes are bound by instruction issue and the L1 data pipe "
+                              "(density: issue 73 %, L1 wavefronts 80 % of peak), not by HBM",
+                "step_achieved_gbs": B_ALG_STEP * value / 1e9, "step_frac": B_ALG_STEP * value / 1e9 / peak,
+                "step_fp32_tflops": flop["step"] * value / 1e12, "step_fp32_frac": flop["step"] * value / 1e12 / FP32_PEAK_TFLOPS}
+
+    # ---- the weak-scaling series' single-GPU point (config 3 at G = 1: one 8 M block), same run ----
+    weak_base = None
+    if not args.no_weak_base:
+        slab = __import__("importlib").import_module("sph-fluid-simulator_b200.slab")
+        s3 = S.scaled_settings(weak_scaling_block(1)["h"])
+        weak_base = slab.single_gpu_base(S, args, weak_scaling_block, s3, dev, warmup)
+        weak_base["step_hbm_frac"] = weak_base["step_achieved_gbs"] / peak
 
     # ---- CPU baseline on a bounded sample: the same settled state, a few full-size steps ----
     cpu = None
@@ -353,27 +449,37 @@ def run_single_gpu(args):
                "sample": f"{cs} steps of the full {n}-particle settled state (after {args.settle} GPU steps), "
                          f"{sec:.1f} s of wall time"}
 
-    # ---- secondary baseline: the reference's own CUDA path on this GPU (subprocess, bounded) ----
+    # ---- secondary baseline: the reference's own CUDA path on this GPU, on the SAME settled state
+    # (neighbours_max stays below its 32-entry lists there), in a subprocess with a timeout ----
     ref_cuda = None
     if not args.no_cpu_baseline:
+        import tempfile
         try:
-            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_reference_cuda.py")],
-                                 capture_output=True, text=True, timeout=180)
-            rows = [l for l in out.stdout.splitlines() if l.startswith("{")]
-            ref_cuda = json.loads(rows[-1]) if rows else {"unavailable": (out.stderr or "no output")[-200:]}
+            with tempfile.TemporaryDirectory() as d:
+                f = os.path.join(d, "settled.npz")
+                np.savez(f, pos=settled["pos"], vel=settled["vel"])
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_reference_cuda.py"), "--state", f,
+                                      "--h", str(scene["h"]), "--steps", "10", "--neighbours-max", str(int(counts.max()))],
+                                     capture_output=True, text=True, timeout=240)
+            rws = [l for l in out.stdout.splitlines() if l.startswith("{")]
+            ref_cuda = json.loads(rws[-1]) if rws else {"unavailable": (out.stderr or "no output")[-200:]}
         except Exception as e:  # noqa: BLE001 - a crash of that code must not take the bench down
             ref_cuda = {"unavailable": repr(e)[:200]}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": warmup,
         "ms_per_step": float(step_ms.mean()), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": scene["name"], "particles": n, "h": scene["h"], "dt": s.dt, "lattice": [nx, ny, nz],
                    "settle_steps": args.settle, "l2": "flushed between timed steps (256 MiB memset outside the event pair)",
-                   "neighbours_mean": float(counts.mean()), "neighbours_max": int(counts.max()),
+                   "steps_per_second": 1e3 / float(step_ms.mean()),
+                   "neighbours_mean": nb_mean, "neighbours_max": int(counts.max()), "candidates_mean": cand_mean,
                    "mean_density": st1.mean_density, "grid_dim": list(st1.grid_dim), "grid_cells": int(st1.grid_cells),
                    "nan_count": int(st1.nan_count), "value_l2_warm": warm_value,
-                   "ms_per_step_p50": float(np.median(step_ms)), "ms_per_step_max": float(step_ms.max())},
+                   "ms_per_step_p50": float(np.median(step_ms)), "ms_per_step_max": float(step_ms.max()),
+                   "timed_call": "sph_step(h, dt, 1) per step: one captured CUDA graph (9 kernels) replayed per call",
+                   "weak_scaling_base": weak_base,
+                   "reference_cuda_baseline": ref_cuda},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60 * n, "d2h_bytes_per_step": 124 * n,
                 "steps": e2e_steps, "call": "sph_update_particles_aos (60-byte Particle rows + mat4 transforms, pinned host memory)",
@@ -381,16 +487,23 @@ def run_single_gpu(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "reference_cuda_baseline": ref_cuda,
     }
     print(json.dumps(line), flush=True)
-    sim.close()
+
+
+def cpu_sample_for(args):
+    """cpu_baseline of an N > 1 line: the reference CPU step on a bounded slice of that line's lattice."""
+    def sample(scene, s):
+        kind, cores, time_steps = reference_step_fn()
+        n, sec, dt, text = reference_sample(scene, time_steps, min(args.settle, 100), 1, 4, args.multi_cpu_budget_s)
+        return {"value": n * 4 / sec, "unit": UNIT, "cores": cores, "kind": kind, "sample": text}
+    return sample
 
 
 def run_multi_gpu(args):
     slab = __import__("importlib").import_module("sph-fluid-simulator_b200.slab")
     scene_fn = dam_break_16m if args.workload == "dam-break-16M" else weak_scaling_block
-    slab.bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks)
+    slab.bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sample_for(args))
 
 
 def main():
@@ -403,12 +516,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--settle", type=int, default=600, help="untimed steps that let the lattice collapse before timing")
-    ap.add_argument("--settle-reference", type=int, default=300)
     ap.add_argument("--reference-budget-s", type=float, default=150.0)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-weak-base", action="store_true", help="skip the single-GPU run of the per-GPU workload at N>1")
+    ap.add_argument("--no-weak-base", action="store_true", help="skip the single-GPU run of the weak-scaling per-GPU workload")
+    ap.add_argument("--no-slab-parity", action="store_true", help="skip the cross-GPU bit-parity check of the N>1 lines")
+    ap.add_argument("--multi-cpu-budget-s", type=float, default=25.0, help="CPU seconds for the cpu_baseline of an N>1 line")
     ap.add_argument("--workload", default="auto", choices=["auto", "dam-break-1M", "weak", "dam-break-16M"],
                     help="auto: config 1 at N=1, config 3 (weak scaling, 8 M particles per GPU) at N>1; "
                          "dam-break-16M: config 2 through the slab driver (strong scaling, any N)")

@@ -180,6 +180,11 @@ int sph_neighbor_lists(sph_handle *h, uint32_t *host_counts, uint64_t *host_offs
 
 int sph_get_stats(sph_handle *h, sph_stats *out);
 
+/* Work statistics of the last step for the bench's FP32 model: the number of candidate
+ * rows the neighbour passes looked at (sum over owned rows of the rows in their 27 cells, the row itself
+ * included) and the number of owned rows. Accepted neighbours come from sph_neighbor_lists. */
+int sph_candidate_count(sph_handle *h, uint64_t *candidates_out, uint64_t *rows_out);
+
 /* Per-pass device times (replaces the Timer blocks of src/sph.cpp:235,249,262). While enabled,
  * every step records CUDA events between its passes; sph_pass_times synchronises, returns the
  * MEAN milliseconds per step over the steps recorded since the last call (or since enabling) in

@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
         "sph_hash_table": ([hp, u32p], C.c_int),
         "sph_neighbor_lists": ([hp, u32p, u64p, u32p, C.c_uint64, u32p], C.c_int),
         "sph_get_stats": ([hp, C.POINTER(Stats)], C.c_int),
+        "sph_candidate_count": ([hp, u64p, u64p], C.c_int),
         "sph_enable_pass_timing": ([hp, C.c_int], C.c_int),
         "sph_pass_times": ([hp, fp, u64p], C.c_int),
         "sph_launch_count": ([hp], C.c_uint64),
@@ -336,6 +337,12 @@ class Sim:
         st = Stats()
         self._ck(self.lib.sph_get_stats(self._h, C.byref(st)))
         return st
+
+    def candidates_mean(self) -> float:
+        """Mean number of candidate rows per owned row in the last step (rows of the 27 cells, self included)."""
+        c, r = C.c_uint64(0), C.c_uint64(0)
+        self._ck(self.lib.sph_candidate_count(self._h, C.byref(c), C.byref(r)))
+        return c.value / max(r.value, 1)
 
     def enable_pass_timing(self, on=True):
         self._ck(self.lib.sph_enable_pass_timing(self._h, int(on)))

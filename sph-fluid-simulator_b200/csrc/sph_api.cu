@@ -69,6 +69,7 @@ struct sph_handle {
     P2PLayout p2p{};
     uint64_t p2p_H = 0, p2p_M = 0;
     uint32_t p2p_epoch = 0;
+    bool p2p_clean = false;   // the peer step's device cursors / done-counters are zero (it re-zeroes them itself)
     int forces_cfg = 0, density_cfg = 0;
     // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
     // are in the cell order of the last build, i.e. from a slab force step until anything else touches them.
@@ -222,12 +223,12 @@ int resolve_rows(sph_handle *h)
     const uint32_t err = h->pinned_rows[1];
     if (err)
         return fail(h, SPH_ERR_CAPACITY,
-                    "slab exchange violation in the previous step:%s%s%s (raise the message capacities or rebalance with the "
+                    "slab exchange violation in an earlier step:%s%s%s%s (raise the message capacities or rebalance with the "
                     "general path)",
                     (err & SLAB_ERR_MIGRANT_OVERFLOW) ? " migrant message overflow" : "",
                     (err & SLAB_ERR_HALO_OVERFLOW) ? " halo message overflow" : "",
-                    (err & SLAB_ERR_NOT_ADJACENT) ? " a particle left for a non-adjacent slab" : "");
-    // (SLAB_ERR_P2P_TIMEOUT is reported through the same bits: a neighbour never raised its flag)
+                    (err & SLAB_ERR_NOT_ADJACENT) ? " a particle left for a non-adjacent slab" : "",
+                    (err & SLAB_ERR_P2P_TIMEOUT) ? " a neighbour never raised its mailbox flag (time-out)" : "");
     return SPH_OK;
 }
 
@@ -270,13 +271,12 @@ int build_grid(sph_handle *h)
     k_scan_exclusive<<<h->num_sms * 4, SCAN_THREADS, 0, s>>>(h->cells, &h->gd->ncells, h->tile_state,
                                                             &h->ctr->ticket, &h->ctr->epoch);
     CK_STEP_LAUNCH();
-    k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot);
+    k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot, h->gd,
+                                                                   h->slab_mode ? h->ctr : nullptr);
     CK_STEP_LAUNCH();
     uint32_t n_sorted = n;
     const uint32_t *n_dev = nullptr;
     if (h->slab_mode) {
-        k_publish_rows<<<1, 32, 0, s>>>(h->cells, h->gd, h->ctr);
-        CK_STEP_LAUNCH();
         if (h->slab_fast) {
             // No host sync: later kernels run over the bound n and skip the dropped tail; the exact
             // count (and the violation bits next to it) reach the host before the next step.
@@ -516,7 +516,7 @@ int build_hash16_order(sph_handle *h, bool need_map)
     CK_LAUNCH();
     if (need_map && n) {
         k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->h16_cells,
-                                                                   h->slot);
+                                                                   h->slot, nullptr, nullptr);
         CK_LAUNCH();
         k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot, h->cell_rank, n, h->h16_cells,
                                                                           h->map, nullptr);
@@ -535,6 +535,7 @@ int after_upload(sph_handle *h, uint64_t n)
     h->n_ghost = 0;
     h->ghost_n[0] = h->ghost_n[1] = h->halo_n[0] = h->halo_n[1] = 0;
     h->have_bbox_from_integration = false;
+    CK(cudaMemsetAsync(&h->ctr->aux[3], 0, sizeof(uint32_t), h->stream));  // slab violation word
     return compute_bbox(h);
 }
 
@@ -1075,6 +1076,28 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     return SPH_OK;
 }
 
+int sph_candidate_count(sph_handle *h, uint64_t *candidates_out, uint64_t *rows_out)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (!candidates_out || !rows_out) return fail(h, SPH_ERR_INVALID, "NULL argument");
+    if (!h->have_step) return fail(h, SPH_ERR_STATE, "candidates are those of the last step: take a step first");
+    rc = ensure_scratch(h, 256);
+    if (rc) return rc;
+    unsigned long long *d = (unsigned long long *)h->scratch;
+    CK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), h->stream));
+    // the start-of-step rows (the cell order h->cells describes) are in the non-current buffers after a step
+    k_candidate_count<<<blocks_for(h->n, PHYS_THREADS), PHYS_THREADS, 0, h->stream>>>(h->pos[h->cur ^ 1], (uint32_t)h->n, h->gd,
+                                                                                     h->cells, h->P.h, d);
+    CK_LAUNCH();
+    unsigned long long out[2] = {0, 0};
+    CK(cudaMemcpyAsync(out, d, sizeof out, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *candidates_out = out[0];
+    *rows_out = out[1];
+    return SPH_OK;
+}
+
 int sph_enable_pass_timing(sph_handle *h, int enable)
 {
     if (!h) return SPH_ERR_INVALID;
@@ -1242,6 +1265,8 @@ int sph_slab_pack(sph_handle *h, const int32_t *cuts, int world, int self, void 
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, c, self, off, cursors, (float4 *)dev_buf);
         CK_LAUNCH();
     }
+    // a general step starts from a clean violation word (the sync-free steps only ever set bits in it)
+    CK(cudaMemsetAsync(&h->ctr->aux[3], 0, sizeof(uint32_t), h->stream));
     h->n_ghost = 0;  // last step's ghosts are dropped rows now
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
@@ -1282,6 +1307,7 @@ int sph_slab_pack_halo(sph_handle *h, int32_t cell_x, int side, void *dev_buf, u
     if (rc) return rc;
     if (side < 0 || side > 1 || !nrows_out) return fail(h, SPH_ERR_INVALID, "bad side / nrows_out");
     unsigned long long *cursor = h->slab_counts + 2 * SLAB_MAX_RANKS + side;
+    h->p2p_clean = false;
     CK(cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), h->stream));
     if (h->n) {
         k_slab_pack_halo<<<blocks_for(h->n, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
@@ -1457,6 +1483,7 @@ int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, 
     if (cap_rows == 0 || cap_rows > h->cap) return fail(h, SPH_ERR_INVALID, "bad message capacity");
     cudaStream_t s = h->stream;
     unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;  // [0,1] migrants, [2,3] halos
+    h->p2p_clean = false;
     CK(cudaMemsetAsync(cur, 0, 4 * sizeof(unsigned long long), s));
     CK(cudaMemsetAsync(&h->ctr->aux[3], 0, sizeof(uint32_t), s));
     if (dev_send_left) CK(cudaMemsetAsync(dev_send_left, 0xFF, cap_rows * 32, s));
@@ -1466,7 +1493,7 @@ int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, 
         k_slab_fast_begin<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dev_send_left ? lo : -0x7fffffff - 1,
             dev_send_right ? hi : 0x7fffffff, lo_prev, hi_next, (uint32_t)cap_rows, (float4 *)dev_send_left,
-            (float4 *)dev_send_right, cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all);
+            (float4 *)dev_send_right, cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all, P2PPublish{});
         CK_LAUNCH();
     }
     h->slab_fast = true;
@@ -1516,7 +1543,7 @@ int sph_slab_fast_halo(sph_handle *h, int32_t lo, int32_t hi, uint64_t cap_rows,
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dev_send_left != nullptr,
             dev_send_right != nullptr, (uint32_t)cap_rows, (float4 *)dev_send_left, (float4 *)dev_send_right,
             h->halo_rows[0], h->halo_rows[1], h->slab_counts + 2 * SLAB_MAX_RANKS, &h->ctr->aux[3], h->gd, h->cells,
-            h->ctr, (uint32_t)h->edge_sorted, h->edge_all);
+            h->ctr, (uint32_t)h->edge_sorted, h->edge_all, P2PPublish{});
         CK_LAUNCH();
     }
     h->fast_halo_cap = cap_rows;
@@ -1621,6 +1648,23 @@ namespace {
 inline char *peer_slot(sph_handle *h, int to_side, unsigned long long off) { return h->peer_mailbox[to_side] + off; }
 }  // namespace
 
+// What the last block of a pack kernel of message type `type` publishes to the two neighbours.
+static P2PPublish p2p_publish_desc(sph_handle *h, int type)
+{
+    const P2PLayout &L = h->p2p;
+    const int b = h->p2p_epoch & 1;
+    P2PPublish pub{};
+    for (int side = 0; side < 2; ++side)
+        if (h->peer_mailbox[side]) {
+            pub.peer_count[side] = (uint32_t *)peer_slot(h, side, L.count[side ^ 1][type][b]);
+            pub.peer_flag[side] = (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][type]);
+        }
+    pub.done = reinterpret_cast<unsigned int *>(h->slab_counts + 2 * SLAB_MAX_RANKS + P2P_CUR_WORDS) + type;
+    pub.epoch = h->p2p_epoch;
+    pub.cap = (uint32_t)(type == P2P_MIG ? h->p2p_M : h->p2p_H);
+    return pub;
+}
+
 int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next)
 {
     int rc = enter_exact(h);
@@ -1631,53 +1675,60 @@ int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, i
     const int b = h->p2p_epoch & 1;
     const P2PLayout &L = h->p2p;
     unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
-    CK(cudaMemsetAsync(cur, 0, 4 * sizeof(unsigned long long), s));
-    CK(cudaMemsetAsync(&h->ctr->aux[3], 0, sizeof(uint32_t), s));
+    if (!h->p2p_clean) {  // first peer step, or the general path used these words since: the step itself re-zeroes them
+        CK(cudaMemsetAsync(cur, 0, (P2P_CUR_WORDS + P2P_DONE_WORDS / 2) * sizeof(unsigned long long), s));
+        h->p2p_clean = true;
+    }
+    // The violation word (aux[3]) is NOT cleared here: a time-out raised by the density leg of the previous
+    // step — after that step's copy to the host — is picked up by this step's copy and reported by the next.
     float4 *dst[2] = {nullptr, nullptr};
     for (int side = 0; side < 2; ++side)
         if (h->peer_mailbox[side]) dst[side] = (float4 *)peer_slot(h, side, L.mig[side ^ 1][b]);
     begin_edge_scans(h);
     if (h->n) {
+        // migrants stored straight into the neighbours' mailboxes; the last block publishes counts and flags
         k_slab_fast_begin<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dst[0] ? lo : -0x7fffffff - 1, dst[1] ? hi : 0x7fffffff,
-            lo_prev, hi_next, (uint32_t)h->p2p_M, dst[0], dst[1], cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all);
-        CK_LAUNCH();
+            lo_prev, hi_next, (uint32_t)h->p2p_M, dst[0], dst[1], cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all,
+            p2p_publish_desc(h, P2P_MIG));
+        CK_STEP_LAUNCH();
+    } else {
+        return fail(h, SPH_ERR_STATE, "a peer step needs at least one row on every rank");
     }
-    for (int side = 0; side < 2; ++side)
-        if (h->peer_mailbox[side]) {
-            k_p2p_publish<<<1, 32, 0, s>>>((uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_MIG][b]), cur + side,
-                                          (uint32_t)h->p2p_M, (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][P2P_MIG]),
-                                          h->p2p_epoch);
-            CK_LAUNCH();
-        }
     h->slab_fast = true;
     h->n_ghost = 0;
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
-    h->launches += 3;
     return SPH_OK;
 }
 
+// Both incoming messages of one type appended behind the current rows by one kernel that waits for the flags.
 static int p2p_append(sph_handle *h, int type, bool ghost)
 {
     const P2PLayout &L = h->p2p;
     const int b = h->p2p_epoch & 1;
     const uint64_t cap = type == P2P_MIG ? h->p2p_M : h->p2p_H;
     const unsigned long long (*buf)[2] = type == P2P_MIG ? L.mig : L.halo;
+    P2PIncoming in{};
+    int nsides = 0;
     for (int side = 0; side < 2; ++side) {
         if (ghost) { h->ghost_first[side] = h->n; h->ghost_n[side] = h->peer_mailbox[side] ? cap : 0; }
         if (!h->peer_mailbox[side]) continue;
         if (h->n + cap > h->cap)
             return fail(h, SPH_ERR_CAPACITY, "appending a %llu-row message to %llu rows exceeds capacity %llu",
                         (unsigned long long)cap, (unsigned long long)h->n, (unsigned long long)h->cap);
-        k_p2p_wait<<<1, 32, 0, h->stream>>>((const uint32_t *)(h->mailbox + L.flag[side][type]), h->p2p_epoch, &h->ctr->aux[3]);
-        CK_LAUNCH();
-        k_slab_append_counted<<<blocks_for(cap, SLAB_THREADS), SLAB_THREADS, 0, h->stream>>>(
-            (const float4 *)(h->mailbox + buf[side][b]), (const uint32_t *)(h->mailbox + L.count[side][type][b]),
-            (uint32_t)cap, (uint32_t)h->n, ghost, h->pos[h->cur], h->vel[h->cur]);
-        CK_LAUNCH();
+        in.rows[side] = (const float4 *)(h->mailbox + buf[side][b]);
+        in.count[side] = (const uint32_t *)(h->mailbox + L.count[side][type][b]);
+        in.flag[side] = (const uint32_t *)(h->mailbox + L.flag[side][type]);
+        in.first[side] = (uint32_t)h->n;
         h->n += cap;
-        h->launches += 2;
+        ++nsides;
+    }
+    if (nsides) {
+        // few blocks (they all poll the flag word first, see p2p_wait_flag): one per SM over the two sides
+        k_p2p_append<<<dim3(std::min(blocks_for(cap, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2), 2), SLAB_THREADS, 0, h->stream>>>(
+            in, (uint32_t)cap, h->p2p_epoch, ghost, h->pos[h->cur], h->vel[h->cur], &h->ctr->aux[3]);
+        CK_STEP_LAUNCH();
     }
     return SPH_OK;
 }
@@ -1704,18 +1755,10 @@ int sph_slab_p2p_halo(sph_handle *h, int32_t lo, int32_t hi)
         k_slab_fast_halo<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dst[0] != nullptr, dst[1] != nullptr,
             (uint32_t)h->p2p_H, dst[0], dst[1], h->halo_rows[0], h->halo_rows[1], cur, &h->ctr->aux[3], h->gd, h->cells,
-            h->ctr, (uint32_t)h->edge_sorted, h->edge_all);
-        CK_LAUNCH();
+            h->ctr, (uint32_t)h->edge_sorted, h->edge_all, p2p_publish_desc(h, P2P_HALO));
+        CK_STEP_LAUNCH();
     }
-    for (int side = 0; side < 2; ++side)
-        if (h->peer_mailbox[side]) {
-            k_p2p_publish<<<1, 32, 0, s>>>((uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_HALO][b]), cur + 2 + side,
-                                          (uint32_t)h->p2p_H, (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][P2P_HALO]),
-                                          h->p2p_epoch);
-            CK_LAUNCH();
-        }
     h->fast_halo_cap = h->p2p_H;
-    h->launches += 3;
     return SPH_OK;
 }
 
@@ -1736,26 +1779,24 @@ int sph_slab_p2p_density(sph_handle *h)
     const int b = h->p2p_epoch & 1;
     const uint32_t cap = (uint32_t)h->p2p_H;
     unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
+    if (!h->peer_mailbox[0] && !h->peer_mailbox[1]) return SPH_OK;
+    float *out[2] = {nullptr, nullptr};
+    P2PRhoIncoming in{};
     for (int side = 0; side < 2; ++side) {
         if (!h->peer_mailbox[side]) continue;
-        k_slab_fast_pack_density<<<blocks_for(cap, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
-            h->vel[h->cur], h->inverse, h->halo_rows[side], cur + 2 + side, cap, (float *)peer_slot(h, side, L.rho[side ^ 1][b]));
-        CK_LAUNCH();
-        k_p2p_publish<<<1, 32, 0, s>>>((uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_RHO][b]), cur + 2 + side, cap,
-                                      (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][P2P_RHO]), h->p2p_epoch);
-        CK_LAUNCH();
-        h->launches += 2;
+        out[side] = (float *)peer_slot(h, side, L.rho[side ^ 1][b]);
+        if (h->ghost_n[side] == 0) continue;
+        in.rho[side] = (const float *)(h->mailbox + L.rho[side][b]);
+        in.count[side] = (const uint32_t *)(h->mailbox + L.count[side][P2P_RHO][b]);
+        in.flag[side] = (const uint32_t *)(h->mailbox + L.flag[side][P2P_RHO]);
+        in.first[side] = (uint32_t)h->ghost_first[side];
     }
-    for (int side = 0; side < 2; ++side) {
-        if (!h->peer_mailbox[side] || h->ghost_n[side] == 0) continue;
-        k_p2p_wait<<<1, 32, 0, s>>>((const uint32_t *)(h->mailbox + L.flag[side][P2P_RHO]), h->p2p_epoch, &h->ctr->aux[3]);
-        CK_LAUNCH();
-        k_slab_set_ghost_density_counted<<<blocks_for(cap, SLAB_THREADS), SLAB_THREADS, 0, s>>>(
-            h->vel[h->cur], h->inverse, (uint32_t)h->ghost_first[side], (const uint32_t *)(h->mailbox + L.count[side][P2P_RHO][b]),
-            cap, (const float *)(h->mailbox + L.rho[side][b]));
-        CK_LAUNCH();
-        h->launches += 2;
-    }
+    k_p2p_rho_pack<<<dim3(blocks_for(cap, SLAB_THREADS), 2), SLAB_THREADS, 0, s>>>(
+        h->vel[h->cur], h->inverse, h->halo_rows[0], h->halo_rows[1], cur, cap, out[0], out[1], p2p_publish_desc(h, P2P_RHO));
+    CK_STEP_LAUNCH();
+    k_p2p_rho_apply<<<dim3(std::min(blocks_for(cap, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2), 2), SLAB_THREADS, 0, s>>>(in, cap, h->p2p_epoch, h->vel[h->cur],
+                                                                                   h->inverse, &h->ctr->aux[3], cur);
+    CK_STEP_LAUNCH();
     return SPH_OK;
 }
 

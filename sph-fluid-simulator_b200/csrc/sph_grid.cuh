@@ -345,9 +345,13 @@ __global__ void k_scan_arm(uint32_t *ticket, uint32_t *epoch)
 // atomicAdd, so the order inside a cell segment is arbitrary at this point.
 __global__ void __launch_bounds__(GRID_THREADS)
 k_place(const uint2 *__restrict__ cell_rank, const float4 *__restrict__ pos, uint32_t n,
-        const uint32_t *__restrict__ starts, uint2 *__restrict__ slot)
+        const uint32_t *__restrict__ starts, uint2 *__restrict__ slot, const GridDesc *__restrict__ gd,
+        StepCounters *publish_rows)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // slab mode: the rows that survive the build (= the scan's end sentinel) are published for the gather
+    // kernel and for the host (this used to be a one-thread kernel of its own)
+    if (publish_rows && i == 0) publish_rows->aux[2] = starts[gd->ncells];
     if (i >= n) return;
     const uint2 cr = cell_rank[i];
     if (cr.x == CELL_NONE) return;
@@ -401,12 +405,6 @@ k_order_gather(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_ra
     vel_out[k] = vel_in[me.x];
     hash_out[k] = hash16_of(cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h));
     if (inverse) inverse[me.x] = k;
-}
-
-// Rows that survived the build (= the scan's end sentinel), published for the host.
-__global__ void k_publish_rows(const uint32_t *__restrict__ starts, const GridDesc *__restrict__ gd, StepCounters *ctr)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) ctr->aux[2] = starts[gd->ncells];
 }
 
 }  // namespace sphb

@@ -106,6 +106,63 @@ k_slab_append(const float4 *__restrict__ rows, uint32_t nrows, uint32_t first, b
 
 // Violation bits accumulated in StepCounters::aux[3] and read back one step late.
 constexpr uint32_t SLAB_ERR_MIGRANT_OVERFLOW = 1u, SLAB_ERR_HALO_OVERFLOW = 2u, SLAB_ERR_NOT_ADJACENT = 4u;
+constexpr uint32_t SLAB_ERR_P2P_TIMEOUT = 8u;
+
+// Peer-memory transport (described at the end of this file): what the LAST block of a pack kernel
+// publishes to the adjacent ranks once every block has stored its rows — the row counts, then, after a
+// system-scope fence, the epoch flags the receivers spin on. done == nullptr: not a peer step.
+struct P2PPublish {
+    uint32_t *peer_count[2];  // [side] row count slot in the neighbour's mailbox (nullptr: no neighbour)
+    uint32_t *peer_flag[2];   // [side] epoch flag in the neighbour's mailbox
+    unsigned int *done;       // blocks of this kernel that have finished (zero at launch)
+    uint32_t epoch, cap;
+};
+
+// Called by every thread at the end of a pack kernel (no thread may have returned early).
+// wrote: this thread stored rows into a peer mailbox.
+__device__ __forceinline__ void p2p_publish_when_last(const P2PPublish &pub, const unsigned long long *cursor_l,
+                                                      const unsigned long long *cursor_r, bool wrote)
+{
+    if (!pub.done) return;
+    if (wrote) __threadfence_system();  // my rows are visible to the peer before anything ordered after this
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence();
+    if (atomicAdd(pub.done, 1u) != gridDim.x * gridDim.y - 1u) return;
+    __threadfence();  // every other block's cursor updates and fences are behind us
+    const unsigned long long *cur[2] = {cursor_l, cursor_r};
+#pragma unroll
+    for (int side = 0; side < 2; ++side)
+        if (pub.peer_count[side]) {
+            const unsigned long long c = __ldcg(cur[side]);
+            *pub.peer_count[side] = (uint32_t)(c < pub.cap ? c : pub.cap);
+        }
+    __threadfence_system();
+#pragma unroll
+    for (int side = 0; side < 2; ++side)
+        if (pub.peer_flag[side]) *reinterpret_cast<volatile uint32_t *>(pub.peer_flag[side]) = pub.epoch;
+}
+
+// First thing a consuming block does: thread 0 spins until the local flag reaches the epoch (gives up
+// after ~4 s and records it), then the block proceeds. The consuming kernels run FEW blocks (grid-stride
+// over the message): every block polls the same word, and a thousand pollers on one L2 line starve the
+// neighbour's incoming store of that very word (measured: 7.8 ms per step with one block per 256 rows).
+__device__ __forceinline__ void p2p_wait_flag(const uint32_t *flag, uint32_t epoch, uint32_t *err)
+{
+    if (threadIdx.x == 0) {
+        const volatile uint32_t *f = flag;
+        const long long t0 = clock64();
+        while ((int)(*f - epoch) < 0) {
+            __nanosleep(500);
+            if (clock64() - t0 > 8000000000ll) {
+                atomicOr(err, SLAB_ERR_P2P_TIMEOUT);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+}
 
 // ---- edge scans ---------------------------------------------------------------------------------
 //
@@ -155,13 +212,15 @@ __global__ void __launch_bounds__(SLAB_THREADS)
 k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int lo, int hi,
                   int lo_prev, int hi_next, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
                   unsigned long long *__restrict__ cur, uint32_t *__restrict__ err, const GridDesc *__restrict__ gd,
-                  const uint32_t *__restrict__ starts, const StepCounters *__restrict__ ctr, bool all)
+                  const uint32_t *__restrict__ starts, const StepCounters *__restrict__ ctr, bool all,
+                  const P2PPublish pub)
 {
     __shared__ EdgeScan s_e;
     if (threadIdx.x == 0) edge_scan_plan(s_e, *gd, starts, n, n, lo, hi, 1, all || ctr->fast_x != 0u);
     __syncthreads();
     const EdgeScan e = s_e;
     const uint32_t total = e.len[0] + e.len[1] + e.len[2];
+    bool wrote = false;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const uint32_t i = edge_scan_row(e, t);
         float4 p = pos[i];
@@ -185,6 +244,7 @@ k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint
                         dst[2 * k] = p;
                         dst[2 * k + 1] = v;
                         drop = true;
+                        wrote = true;
                     }
                 }
             }
@@ -194,6 +254,7 @@ k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint
             pos[i] = p;
         }
     }
+    p2p_publish_when_last(pub, &cur[0], &cur[1], wrote);
 }
 
 // Both halo messages in one pass over the edge rows (two layers deep: a row of layer lo + 1 may have
@@ -205,13 +266,14 @@ k_slab_fast_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
                  bool has_left, bool has_right, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
                  uint32_t *__restrict__ rows_l, uint32_t *__restrict__ rows_r, unsigned long long *__restrict__ cur,
                  uint32_t *__restrict__ err, const GridDesc *__restrict__ gd, const uint32_t *__restrict__ starts,
-                 const StepCounters *__restrict__ ctr, uint32_t sorted, bool all)
+                 const StepCounters *__restrict__ ctr, uint32_t sorted, bool all, const P2PPublish pub)
 {
     __shared__ EdgeScan s_e;
     if (threadIdx.x == 0) edge_scan_plan(s_e, *gd, starts, n, sorted, lo, hi, 2, all || ctr->fast_x != 0u);
     __syncthreads();
     const EdgeScan e = s_e;
     const uint32_t total = e.len[0] + e.len[1] + e.len[2];
+    bool wrote = false;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const uint32_t i = edge_scan_row(e, t);
         const float4 p = pos[i];
@@ -224,15 +286,16 @@ k_slab_fast_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
         v.w = 0.f;
         if (to_l) {
             const unsigned long long k = atomicAdd(&cur[2], 1ull);
-            if (k < cap) { send_l[2 * k] = p; send_l[2 * k + 1] = v; rows_l[k] = i; }
+            if (k < cap) { send_l[2 * k] = p; send_l[2 * k + 1] = v; rows_l[k] = i; wrote = true; }
             else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
         }
         if (to_r) {
             const unsigned long long k = atomicAdd(&cur[3], 1ull);
-            if (k < cap) { send_r[2 * k] = p; send_r[2 * k + 1] = v; rows_r[k] = i; }
+            if (k < cap) { send_r[2 * k] = p; send_r[2 * k + 1] = v; rows_r[k] = i; wrote = true; }
             else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
         }
     }
+    p2p_publish_when_last(pub, &cur[2], &cur[3], wrote);
 }
 
 // Densities of the rows of one halo message; the message count is on the device (cursor). The
@@ -342,8 +405,6 @@ k_slab_xhist(const float4 *__restrict__ pos, uint32_t n, float h, int x_lo, uint
 // scope and raises the peer's flag to the step epoch; the receiver's stream spins on its own flag
 // before it appends. Two buffers are enough: a sender reaches epoch e+2 only after it has waited
 // for the neighbour's epoch e+1 message, which the neighbour sent after consuming epoch e.
-constexpr uint32_t SLAB_ERR_P2P_TIMEOUT = 8u;
-
 struct P2PLayout {
     unsigned long long mig[2][2], halo[2][2], rho[2][2];  // byte offsets [side][parity]
     unsigned long long count[2][3][2];                     // uint32 [side][type][parity]
@@ -352,59 +413,87 @@ struct P2PLayout {
 };
 enum { P2P_MIG = 0, P2P_HALO = 1, P2P_RHO = 2 };
 
-__global__ void k_p2p_publish(uint32_t *peer_count, const unsigned long long *local_cursor, uint32_t cap,
-                              uint32_t *peer_flag, uint32_t epoch)
+// Device-side scratch of the peer step, in sph_handle::slab_counts behind the general path's counters:
+// cur[0..1] migrant cursors, cur[2..3] halo cursors, then one "blocks done" counter per publishing kernel.
+// All of it is zero when a peer step begins: k_p2p_rho_apply, the last exchange kernel of a step, re-zeroes it.
+constexpr int P2P_CUR_WORDS = 4;  // unsigned long long cursors
+constexpr int P2P_DONE_WORDS = 4; // unsigned int counters after them (migrants, halo, rho, spare)
+
+// Both incoming messages of one type (side = blockIdx.y) appended behind the current rows, each into a
+// fixed region of `cap` rows: rows past the message's count become dropped rows. The block first waits for
+// the neighbour's flag (the flag-wait used to be a kernel of its own).
+struct P2PIncoming {
+    const float4 *rows[2];    // [side] message in the local mailbox (nullptr: no neighbour)
+    const uint32_t *count[2];
+    const uint32_t *flag[2];
+    uint32_t first[2];        // first destination row
+};
+
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_p2p_append(const P2PIncoming in, uint32_t cap, uint32_t epoch, bool ghost, float4 *__restrict__ pos,
+             float4 *__restrict__ vel, uint32_t *err)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const unsigned long long c = *local_cursor;
-    *peer_count = (uint32_t)(c < cap ? c : cap);
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(peer_flag) = epoch;
+    const int side = blockIdx.y;
+    if (!in.rows[side]) return;
+    p2p_wait_flag(in.flag[side], epoch, err);
+    const uint32_t first = in.first[side], count = *in.count[side];
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += gridDim.x * blockDim.x) {
+        if (k >= count) {
+            pos[first + k] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
+            continue;
+        }
+        float4 p = in.rows[side][2 * k];
+        const float4 v = in.rows[side][2 * k + 1];
+        uint32_t w = __float_as_uint(p.w) & W_ID_MASK;
+        if (ghost) w |= W_GHOST;
+        p.w = __uint_as_float(w);
+        pos[first + k] = p;
+        vel[first + k] = v;
+    }
 }
 
-// Spin (one thread) until the local flag reaches the epoch; gives up after ~4 s and records it.
-__global__ void k_p2p_wait(const uint32_t *flag, uint32_t epoch, uint32_t *err)
+// Densities of my boundary rows (the rows of the two halo messages, same order) stored into the
+// neighbours' mailboxes; the last block publishes counts and flags.
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_p2p_rho_pack(const float4 *__restrict__ vel, const uint32_t *__restrict__ inverse, const uint32_t *__restrict__ rows_l,
+               const uint32_t *__restrict__ rows_r, const unsigned long long *__restrict__ cur, uint32_t cap,
+               float *__restrict__ out_l, float *__restrict__ out_r, const P2PPublish pub)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const volatile uint32_t *f = flag;
-    const long long t0 = clock64();
-    while ((int)(*f - epoch) < 0) {
-        __nanosleep(200);
-        if (clock64() - t0 > 8000000000ll) {
-            atomicOr(err, SLAB_ERR_P2P_TIMEOUT);
-            break;
+    const int side = blockIdx.y;
+    float *out = side ? out_r : out_l;
+    bool wrote = false;
+    if (out) {
+        const uint32_t *rows = side ? rows_r : rows_l;
+        const unsigned long long c = cur[2 + side];
+        const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+        if (k < cap && k < c) {
+            out[k] = vel[inverse[rows[k]]].w;
+            wrote = true;
         }
     }
-    __threadfence_system();
+    p2p_publish_when_last(pub, &cur[2], &cur[3], wrote);
 }
 
-// Append a counted message from the local mailbox into a fixed region of `cap` rows: rows past
-// the count become dropped rows.
-__global__ void __launch_bounds__(SLAB_THREADS)
-k_slab_append_counted(const float4 *__restrict__ rows, const uint32_t *__restrict__ count, uint32_t cap, uint32_t first,
-                      bool ghost, float4 *__restrict__ pos, float4 *__restrict__ vel)
-{
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= cap) return;
-    if (k >= *count) {
-        pos[first + k] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
-        return;
-    }
-    float4 p = rows[2 * k];
-    const float4 v = rows[2 * k + 1];
-    uint32_t w = __float_as_uint(p.w) & W_ID_MASK;
-    if (ghost) w |= W_GHOST;
-    p.w = __uint_as_float(w);
-    pos[first + k] = p;
-    vel[first + k] = v;
-}
+// The neighbours' densities into my ghost rows (ghost batch `side` was appended at pre-sort rows
+// [first[side], first[side] + cap)); then the step's cursors and done-counters are zeroed for the next step.
+struct P2PRhoIncoming {
+    const float *rho[2];
+    const uint32_t *count[2];
+    const uint32_t *flag[2];
+    uint32_t first[2];
+};
 
 __global__ void __launch_bounds__(SLAB_THREADS)
-k_slab_set_ghost_density_counted(float4 *__restrict__ vel, const uint32_t *__restrict__ inverse, uint32_t first,
-                                 const uint32_t *__restrict__ count, uint32_t cap, const float *__restrict__ in)
+k_p2p_rho_apply(const P2PRhoIncoming in, uint32_t cap, uint32_t epoch, float4 *__restrict__ vel,
+                const uint32_t *__restrict__ inverse, uint32_t *err, unsigned long long *cur)
 {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < cap && k < *count) vel[inverse[first + k]].w = in[k];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < P2P_CUR_WORDS + P2P_DONE_WORDS / 2) cur[threadIdx.x] = 0ull;
+    const int side = blockIdx.y;
+    if (!in.rho[side]) return;
+    p2p_wait_flag(in.flag[side], epoch, err);
+    const uint32_t count = min(cap, *in.count[side]);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
+        vel[inverse[in.first[side] + k]].w = in.rho[side][k];
 }
 
 }  // namespace sphb

@@ -45,6 +45,7 @@ class GpuEngine:
         self.lib = sim.lib
         self.device = torch.device("cuda", device_index)
         self.stream = torch.cuda.ExternalStream(sim.stream, device=self.device)
+        self.phase_events = None
         self._ck(self.lib.sph_slab_enable(sim.handle, 1))
 
     def _ck(self, rc):
@@ -127,15 +128,43 @@ class GpuEngine:
         buf = (C.c_ubyte * 64)(*handle)
         self._ck(self.lib.sph_slab_p2p_connect(self.sim.handle, side, buf))
 
+    PHASES = ("migrate_out", "migrate_in", "halo_out", "halo_in", "grid+density", "halo_density", "forces")
+
     def p2p_step(self, lo, hi, lo_prev, hi_next, dt):
+        """One peer-mailbox step: 15 kernels, no host synchronisation. With self.phase_events set (a list),
+        CUDA events are recorded on the library's stream between the phases (no synchronisation either)."""
         h, L = self.sim.handle, self.lib
+        ev = None
+        if self.phase_events is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.PHASES) + 1)]
+            self.phase_events.append(ev)
+            ev[0].record(self.stream)
         self._ck(L.sph_slab_p2p_begin(h, int(lo), int(hi), int(lo_prev), int(hi_next)))
+        if ev: ev[1].record(self.stream)
         self._ck(L.sph_slab_p2p_arrivals(h))
+        if ev: ev[2].record(self.stream)
         self._ck(L.sph_slab_p2p_halo(h, int(lo), int(hi)))
+        if ev: ev[3].record(self.stream)
         self._ck(L.sph_slab_p2p_ghosts(h))
+        if ev: ev[4].record(self.stream)
         self._ck(L.sph_slab_step_density(h))
+        if ev: ev[5].record(self.stream)
         self._ck(L.sph_slab_p2p_density(h))
+        if ev: ev[6].record(self.stream)
         self._ck(L.sph_slab_step_forces(h, C.c_float(dt)))
+        if ev: ev[7].record(self.stream)
+
+    def phase_ms(self):
+        """Mean milliseconds per step of each phase over the steps recorded in self.phase_events (synchronises)."""
+        evs = self.phase_events or []
+        if not evs:
+            return {}
+        self.sim.sync()
+        acc = [0.0] * len(self.PHASES)
+        for ev in evs:
+            for k in range(len(self.PHASES)):
+                acc[k] += ev[k].elapsed_time(ev[k + 1])
+        return {name: acc[k] / len(evs) for k, name in enumerate(self.PHASES)}
 
     # -- sync-free path: fixed-size messages, tensors may be None (no neighbour on that side) --------
     @staticmethod
@@ -213,6 +242,7 @@ class SlabDriver:
         self.backend = dist.get_backend(group) if world > 1 else "none"
         self.cuts = [INT_MIN] + [INT_MAX] * world if world == 1 else None
         self.stats = {"migrated_rows": 0, "halo_rows": 0, "steps": 0}
+        self.last_imbalance = 0.0
         # SLAB_PROFILE=1: synchronise after every phase and accumulate wall-clock per phase
         self.profile = os.environ.get("SLAB_PROFILE") == "1"
         self.phase_s = {}
@@ -269,6 +299,48 @@ class SlabDriver:
             dist.all_reduce(hist, group=self.group)
             self.cuts = choose_cuts(hist.cpu().numpy(), self.x_lo, self.world)
         return self.cuts
+
+    def global_histogram(self):
+        """All-reduced histogram of cell.x over owned rows (host array; synchronises; collective)."""
+        with self._in_stream():
+            hist = torch.from_numpy(self.e.xcell_histogram(self.x_lo, self.nbins))
+            if self.world > 1:
+                if self.backend == "nccl":
+                    hist = hist.to(self.e.device)
+                dist.all_reduce(hist, group=self.group)
+            return hist.cpu().numpy()
+
+    def slab_counts(self, hist, cuts=None):
+        """Particles per slab under `cuts` from a global histogram."""
+        cuts = self.cuts if cuts is None else cuts
+        edges = [0] + [int(min(max(c - self.x_lo, 0), len(hist))) for c in cuts[1:-1]] + [len(hist)]
+        return np.array([int(hist[edges[k]:edges[k + 1]].sum()) for k in range(self.world)], dtype=np.int64)
+
+    def rebalance_incremental(self, threshold: float = 0.05):
+        """Move every interior cut by at most ONE cell towards its balanced position, and only when the
+        fullest slab exceeds the mean by more than `threshold`. A one-cell move is something the sync-free
+        steps handle by themselves (the rows of the layer that changed hands are ordinary migrants to the
+        adjacent rank), so no general all-to-all step is needed afterwards. Returns True when cuts moved.
+        Collective; one host synchronisation."""
+        if self.world == 1:
+            return False
+        hist = self.global_histogram()
+        counts = self.slab_counts(hist)
+        mean = counts.sum() / self.world
+        self.last_imbalance = float(counts.max() / mean - 1.0) if mean > 0 else 0.0
+        if self.last_imbalance <= threshold:
+            return False
+        target = choose_cuts(hist, self.x_lo, self.world)
+        new = list(self.cuts)
+        for k in range(1, self.world):
+            step = int(np.sign(target[k] - self.cuts[k]))
+            new[k] = self.cuts[k] + step
+        for k in range(1, self.world):  # keep at least one x-cell per slab
+            lo = (new[k - 1] + 1) if k > 1 else INT_MIN
+            new[k] = max(new[k], lo)
+        moved = new != list(self.cuts)
+        self.cuts = new
+        return moved
 
     # -- one step ----------------------------------------------------------------------------
     def step(self, dt: float = 0.0):
@@ -475,9 +547,121 @@ def gather_owned(sim, fields=("pos", "vel", "density", "force", "hash")):
 
 
 # ------------------------------------------------------------------------------------------------
-# bench: weak scaling (config 3), called from bench.py
+# steady-state runner + in-job parity check + bench (configs 2 and 3), called from bench.py
 # ------------------------------------------------------------------------------------------------
-def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
+class SlabRunner:
+    """Steps a SlabDriver in steady state. The step counter is persistent across run() calls: the one
+    general (all-to-all) step that delivers the initial rows happens once, at step 0; afterwards every step
+    is sync-free. Every `check_every` steps the global histogram is looked at (one host synchronisation);
+    cuts only move when the fullest slab exceeds the mean by `threshold`, by one cell per cut, which the
+    sync-free steps absorb as ordinary migration (transport "general" keeps the round-1 behaviour)."""
+
+    def __init__(self, driver, dt, transport="p2p", check_every=200, threshold=0.05, halo_slack=1.5):
+        self.d, self.dt, self.transport = driver, dt, transport
+        self.check_every, self.threshold, self.halo_slack = check_every, threshold, halo_slack
+        self.k = 0
+        self.general_steps = self.cut_moves = self.balance_checks = 0
+
+    def _first_step(self):
+        d = self.d
+        d.rebalance()
+        d.step(self.dt)
+        self.general_steps += 1
+        if d.world > 1 or self.transport != "general":
+            rows = d.suggest_halo_rows(slack=self.halo_slack)
+            if self.transport == "p2p":
+                d.setup_p2p(rows, migrant_rows=rows)  # a whole layer may change hands when a cut moves
+            elif self.transport == "nccl":
+                d.setup_fast(rows, migrant_rows=rows)
+
+    def run(self, steps):
+        d = self.d
+        for _ in range(steps):
+            if self.k == 0:
+                self._first_step()
+            elif self.transport == "general":
+                if self.k % self.check_every == 0:
+                    d.rebalance()
+                d.step(self.dt)
+                self.general_steps += 1
+            else:
+                if self.k % self.check_every == 0 and d.world > 1:
+                    self.balance_checks += 1
+                    self.cut_moves += bool(d.rebalance_incremental(self.threshold))
+                if self.transport == "p2p":
+                    d.step_p2p(self.dt)
+                else:
+                    d.step_fast(self.dt)
+            self.k += 1
+
+
+def slab_parity_check(S, local, rank, world, transport="p2p", steps=4):
+    """Cross-GPU evidence inside the bench job: the 1 M dam break (config 1) settled on every rank's own GPU,
+    then `steps` steps taken twice from that state — on this GPU alone, and slab-split over all ranks with
+    the exchange going through the transport under test — and each rank compares the rows it owns at the
+    end, bit for bit, with its single-GPU result. Returns a short verdict string (same on all ranks)."""
+    h = 0.075
+    sep = h * 16.0 / 15.0
+    nx, ny, nz = 64, 80, 196
+    s = S.scaled_settings(h)
+    pos, vel = S.scene_block(nx, ny, nz, sep, ((h - 8.0) + sep, h * 5.0 / 3.0, -nz * sep / 2.0), h, 1024)
+    n = pos.shape[0]
+    one = S.Sim(s, capacity=n, device=local)
+    one.upload(pos, vel)
+    one.step(450)  # the lattice starts without neighbours: let it collapse into an interacting state first
+    st = one.download(S.ORDER_ID, fields=("pos", "vel"))
+    one.upload(st["pos"], st["vel"])
+    one.step(steps)
+    want = one.download(S.ORDER_ID, fields=("pos", "vel", "density"))
+    interacting = float(one.stats().mean_density)
+    one.close()
+
+    x_lo, nbins = x_cell_range(s)
+    cx = np.trunc(st["pos"][:, 0] / np.float32(h)).astype(np.int64)  # getCell: fp32 divide, truncation
+    hist = np.bincount(np.clip(cx - x_lo, 0, nbins - 1), minlength=nbins)
+    cuts = choose_cuts(hist, x_lo, world)
+    mine = owner_of(cuts, cx) == rank
+    ids = np.arange(n, dtype=np.uint32)
+    drv, sim = make_gpu_driver(s, int(mine.sum() * 1.6) + (1 << 19), local, rank, world)
+    sim.upload(st["pos"][mine], st["vel"][mine], ids[mine])
+    drv.cuts = cuts
+    drv.step(s.dt)  # general step: delivers nothing new here, builds the first halos
+    if world > 1 and transport in ("p2p", "nccl"):
+        rows = drv.suggest_halo_rows(slack=1.5)
+        if transport == "p2p":
+            drv.setup_p2p(rows)
+        else:
+            drv.setup_fast(rows)
+    for _ in range(steps - 1):
+        if world == 1 or transport == "general":
+            drv.step(s.dt)
+        elif transport == "p2p":
+            drv.step_p2p(s.dt)
+        else:
+            drv.step_fast(s.dt)
+    sim.sync()
+    got = gather_owned(sim, fields=("pos", "vel", "density"))
+    i = got["id"]
+    bad = 0
+    for k in ("pos", "vel", "density"):
+        a, b = got[k].view(np.uint32), want[k][i].view(np.uint32)
+        bad += int((a != b).reshape(len(i), -1).any(axis=1).sum())
+    sim.close()
+    t = torch.tensor([bad, len(i)], dtype=torch.int64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t)
+    bad, owned = int(t[0].item()), int(t[1].item())
+    if owned != n:
+        return f"MISMATCH: {owned} rows owned in total, {n} expected"
+    if interacting <= 9.3:
+        return "INCONCLUSIVE: the check state is not interacting"
+    if bad:
+        return f"MISMATCH: {bad} rows differ from the single-GPU run"
+    return (f"bit-identical ({n} particles, {steps} steps, {world} GPUs, transport {transport}: pos, vel, density of every "
+            f"owned row equal to the single-GPU run on the same GPU; mean density {interacting:.3f})")
+
+
+def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sample=None):
     import importlib
     import json
     S = importlib.import_module("sph-fluid-simulator_b200")
@@ -490,35 +674,24 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     scene = scene_fn(world)
     s = S.scaled_settings(scene["h"])
     nx, ny, nz = scene["dims"]
+    transport = os.environ.get("SPH_SLAB_TRANSPORT", "p2p")  # p2p (peer-memory mailboxes) | nccl | general
+    warmup = max(args.warmup, 3)
 
-    # Weak-scaling base: the same per-GPU workload (one 61 x 256 x 512 block) on ONE GPU, measured in
-    # this job on rank 0 with the same settle / warm-up / step counts, so that the scaling series has
-    # a like-for-like N = 1 point (bench.py --gpus 1 runs config 1, the 1 M dam break, instead).
+    # Cross-GPU correctness first: a bench line without it would only show that the step is fast.
+    parity = None
+    if world > 1 and not getattr(args, "no_slab_parity", False):
+        parity = slab_parity_check(S, local, rank, world, transport)
+        torch.cuda.empty_cache()
+        dist.barrier()
+
+    # Scaling base: the same per-GPU workload (for config 3, one 61 x 256 x 512 block) on ONE GPU, measured in
+    # this job on rank 0 with the same settle / warm-up / step counts and the same library calls, so that the
+    # series has a like-for-like N = 1 point (bench.py --gpus 1 reports config 1 and carries this same
+    # measurement as config.weak_scaling_base).
     base = None
     if world > 1 and not getattr(args, "no_weak_base", False):
         if rank == 0:
-            b = scene_fn(1)
-            bx, by, bz = b["dims"]
-            bpos, bvel, bids = S.scene_block_slice(bx, by, bz, b["sep"], b["origin"], b["h"], b["seed"], 0, bx)
-            bdrv, bsim = make_gpu_driver(s, int(bpos.shape[0] * 1.25) + (1 << 20), local, 0, 1)
-            bsim.upload(bpos, bvel, bids)
-            for _ in range(args.settle + max(args.warmup, 3)):
-                bdrv.step(s.dt)
-            bsim.sync()
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            with torch.cuda.stream(bdrv.e.stream):
-                t0.record(bdrv.e.stream)
-            for _ in range(args.steps):
-                bdrv.step(s.dt)
-            with torch.cuda.stream(bdrv.e.stream):
-                t1.record(bdrv.e.stream)
-            bsim.sync()
-            bms = t0.elapsed_time(t1) / args.steps
-            base = {"n_gpus": 1, "particles": int(bpos.shape[0]), "ms_per_step": bms,
-                    "value": bpos.shape[0] / (bms * 1e-3), "workload": b["name"]}
-            bsim.close()
-            del bpos, bvel, bids, bdrv, bsim
-            torch.cuda.empty_cache()
+            base = single_gpu_base(S, args, scene_fn, s, local, warmup)
         dist.barrier()
 
     per = nx // world
@@ -528,31 +701,9 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     driver, sim = make_gpu_driver(s, int(n_local * 1.5) + (1 << 20), local, rank, world)
     sim.upload(pos, vel, ids)
     del pos, vel, ids
-    driver.rebalance()
-
-    transport = os.environ.get("SPH_SLAB_TRANSPORT", "p2p")  # p2p (peer-memory mailboxes) | nccl | general
-
-    def run(steps, rebalance_every=100):
-        # General (synchronous, all-to-all) step right after every change of cuts; in between, the
-        # sync-free step: stores into the neighbours' mailboxes (p2p) or fixed-size NCCL messages.
-        for k in range(steps):
-            if k % rebalance_every == 0 or transport == "general":
-                if world > 1 and k % rebalance_every == 0:
-                    driver.rebalance()
-                driver.step(s.dt)
-                if transport == "p2p" and not getattr(driver, "p2p_ready", False):
-                    driver.setup_p2p(driver.suggest_halo_rows(slack=2.0))
-                elif transport == "nccl":
-                    driver.setup_fast(driver.suggest_halo_rows())
-            elif transport == "p2p":
-                driver.step_p2p(s.dt)
-            else:
-                driver.step_fast(s.dt)
-
-    run(args.settle)
-    if world > 1:
-        driver.rebalance()
-    run(max(args.warmup, 3))
+    runner = SlabRunner(driver, s.dt, transport)
+    runner.run(args.settle)
+    runner.run(warmup)
     sim.sync()
     if world > 1:
         dist.barrier()
@@ -563,17 +714,23 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
     if clocks:
         clocks.start()
     launches0 = sim.launch_count
+    general0 = runner.general_steps
     stream = driver.e.stream
+    if transport == "p2p" and world > 1:
+        driver.e.phase_events = []  # CUDA events between the phases of every timed step (no synchronisation)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         flush.zero_()
         e0.record(stream)
-    run(args.steps)
+    runner.run(args.steps)
     with torch.cuda.stream(stream):
         e1.record(stream)
     sim.sync()
     torch.cuda.synchronize()
+    phase_ms = driver.e.phase_ms()
+    driver.e.phase_events = None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    launches = int(sim.launch_count - launches0)
     st = sim.stats()
     owned = torch.tensor([int(st.count)], dtype=torch.int64, device=f"cuda:{local}")
     if world > 1:
@@ -581,8 +738,12 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
         owned_all = [torch.zeros_like(owned) for _ in range(world)]
         dist.all_gather(owned_all, owned)
         owned_list = [int(o.item()) for o in owned_all]
+        ph = torch.tensor([phase_ms.get(k, 0.0) for k in GpuEngine.PHASES], dtype=torch.float64, device=f"cuda:{local}")
+        ph_max = ph.clone()
+        dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
     else:
         owned_list = [int(owned.item())]
+        ph_max = None
     clk = clocks.stop() if clocks else None
 
     # ---- end to end: every step uploads the rank's rows from pinned host memory, steps through the
@@ -617,15 +778,8 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
             rc = sim.lib.sph_upload(sim.handle, m, pp, pv, pi_)   # pinned host rows -> device
             if rc:
                 raise RuntimeError(sim.lib.sph_last_error(sim.handle).decode())
-            if driver.profile:
-                sim.sync(); t1 = time.perf_counter()
             driver.step(s.dt)
-            if driver.profile:
-                sim.sync(); t2 = time.perf_counter()
             m = read_back()                                       # owned rows -> pinned host
-            if driver.profile:
-                print(f"[rank {rank}] e2e iteration {k}: upload {1e3 * (t1 - t0):.2f} ms, step {1e3 * (t2 - t1):.2f} ms, "
-                      f"download {1e3 * (time.perf_counter() - t2):.2f} ms", file=sys.stderr, flush=True)
             if world > 1:
                 dist.barrier()
             iter_ms.append(1e3 * (time.perf_counter() - t0))
@@ -637,18 +791,26 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
         e2e = {"value": n_total * k_e2e / float(tt.item()), "unit": UNIT, "steps": k_e2e,
                "h2d_bytes_per_step": 28 * n_total, "d2h_bytes_per_step": 28 * n_total,
                "iteration_ms_rank0": [round(v, 2) for v in iter_ms],
-               "call": "per rank: sph_upload(pos, vel, id in pinned host memory) -> slab step (general path) -> "
+               "call": "per rank: sph_upload(pos, vel, id in pinned host memory) -> slab step (general path: an upload "
+                       "resets the resident state, so the all-to-all step delivers and rebuilds the halos) -> "
                        "sph_slab_download_owned(pos, vel, id into pinned host memory)"}
-    if driver.profile:
-        print(f"[rank {rank}] phase ms/step:", {k: round(1e3 * v / max(driver.stats['steps'], 1), 3) for k, v in driver.phase_s.items()},
-              file=sys.stderr, flush=True)
     total_s = float(ms.item()) * 1e-3
     value = n_total * args.steps / total_s
     if rank == 0:
         peak, peak_src = peaks()
+        if base:
+            base["step_hbm_frac"] = base["step_achieved_gbs"] / peak
+        cpu = cpu_sample(scene, s) if (cpu_sample and not args.no_cpu_baseline) else None
+        ms_step = 1e3 * total_s / args.steps
+        phases = None
+        if ph_max is not None:
+            phases = {"rank0": {k: round(phase_ms.get(k, 0.0), 4) for k in GpuEngine.PHASES},
+                      "max_over_ranks": {k: round(float(ph_max[j].item()), 4) for j, k in enumerate(GpuEngine.PHASES)}}
+            slow = max(phases["max_over_ranks"], key=phases["max_over_ranks"].get)
+            phases["limiting_phase"] = slow
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": scene.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": scene["name"], "particles": n_total, "particles_per_gpu": owned_list,
                        "h": scene["h"], "dt": s.dt, "lattice": [nx, ny, nz], "settle_steps": args.settle,
@@ -656,22 +818,60 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks):
                              "L2 flushed once before the timed region",
                        "decomposition": "x slabs; per step: migrants, 1-cell ghost halo and halo densities go to the adjacent "
                                         "ranks with device-resident counts and no host sync; transport = " + transport +
-                                        " (p2p: pack kernels store into the neighbour's CUDA-IPC mailbox over NVLink; "
-                                        "nccl: fixed-size send/recv); general all-to-all step + rebalance every 100 steps",
+                                        " (p2p: pack kernels store into the neighbour's CUDA-IPC mailbox over NVLink and publish "
+                                        "count + flag themselves; nccl: fixed-size send/recv). One general all-to-all step at "
+                                        "step 0 only; cuts are looked at every 200 steps and move by one cell when the fullest "
+                                        "slab exceeds the mean by 5 %",
+                       "general_steps_in_timed_region": runner.general_steps - general0,
+                       "balance_checks": runner.balance_checks, "cut_moves": runner.cut_moves,
+                       "imbalance_at_last_check": driver.last_imbalance,
                        "halo_message_rows": getattr(driver, "fast_H", None),
                        "single_gpu_same_workload": base,
+                       "scaling_efficiency_vs_same_workload": (value / world / base["value"]) if base else None,
+                       "slab_parity": parity,
                        "rank0_mean_density": st.mean_density, "rank0_grid_dim": list(st.grid_dim),
-                       "migrated_rows_rank0": driver.stats["migrated_rows"], "halo_rows_rank0": driver.stats["halo_rows"],
-                       "phase_ms_per_step_rank0": {k: 1e3 * v / max(driver.stats["steps"], 1) for k, v in driver.phase_s.items()}},
+                       "phase_ms_per_step": phases},
             "clocks": clk,
             "e2e": e2e,
-            "gpu_launches": int(sim.launch_count - launches0),
+            "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": 292.0 * value / world / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": 292.0 * value / world / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "note": "per-GPU algorithmic 292 B/particle-step over the step time"},
-            "cpu_baseline": None,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def single_gpu_base(S, args, scene_fn, s, local, warmup):
+    """The per-GPU workload of the scaling series on one GPU through the resident step (sph_step: CUDA-graph
+    replay, as a single-GPU user would run it): settle, warm up, then `steps` steps between two events."""
+    b = scene_fn(1)
+    bx, by, bz = b["dims"]
+    pos, vel = S.scene_block(bx, by, bz, b["sep"], b["origin"], b["h"], b["seed"])
+    n = pos.shape[0]
+    sim = S.Sim(s, capacity=n, device=local)
+    sim.upload(pos, vel)
+    del pos, vel
+    sim.step(args.settle + warmup)
+    sim.sync()
+    stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    sim.step(args.steps)
+    t1.record(stream)
+    sim.sync()
+    ms = t0.elapsed_time(t1) / args.steps
+    sim.enable_pass_timing(True)
+    sim.step(min(args.steps, 20))
+    passes = sim.pass_times()
+    sim.enable_pass_timing(False)
+    st = sim.stats()
+    out = {"n_gpus": 1, "particles": n, "ms_per_step": ms, "value": n / (ms * 1e-3), "workload": b["name"],
+           "pass_ms": {k: v for k, v in passes.items() if k != "steps"}, "mean_density": st.mean_density,
+           "step_achieved_gbs": 292.0 * n / (ms * 1e-3) / 1e9}
+    sim.close()
+    torch.cuda.empty_cache()
+    return out

@@ -58,6 +58,59 @@ def _worker(rank, world, port, steps, rebalance_every, out_dir, fast=False):
     dist.destroy_process_group()
 
 
+def _runner_worker(rank, world, port, steps, out_dir):
+    """SlabRunner in steady state over the sync-free path, starting from deliberately lopsided cuts: the
+    balance check moves every cut one cell at a time and the sync-free steps absorb each move as migration."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.pyoracle import Oracle
+    from slab_cpu_engine import CpuOracleEngine
+    slab = importlib.import_module("sph-fluid-simulator_b200.slab")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cube20_step200.npz"))
+    O = Oracle()
+    s = O.settings(tuple(float(v) for v in g["settings"]))
+    pos, vel = g["pos0"], g["vel0"]
+    ids = np.arange(pos.shape[0], dtype=np.uint32)
+    eng = CpuOracleEngine(O, s)
+    mine = ids % world == rank
+    eng.upload(pos[mine], vel[mine], ids[mine])
+    drv = slab.SlabDriver(eng, rank, world, x_lo=-60, nbins=121)
+    run = slab.SlabRunner(drv, float(g["dt"]), transport="nccl", check_every=1, threshold=0.02, halo_slack=4.0)
+    # lopsided start: balanced cuts shifted two cells to the left (rank 0 gets too little)
+    balanced = drv.rebalance()
+    drv.cuts = [balanced[0]] + [c - 2 for c in balanced[1:-1]] + [balanced[-1]]
+    drv.rebalance = lambda: drv.cuts  # the runner's first step must keep the lopsided cuts
+    first_cuts = list(drv.cuts)
+    run.run(steps)
+    st = eng.owned_state()
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), cuts=np.array(drv.cuts, np.int64), first_cuts=np.array(first_cuts, np.int64),
+             balanced=np.array(balanced, np.int64), general=run.general_steps, moves=run.cut_moves, checks=run.balance_checks, **st)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_runner_rebalances_one_cell_at_a_time_without_general_steps(oracle, world):
+    steps = 6
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_runner_worker, args=(world, _free_port(), steps, d), nprocs=world, join=True)
+        ranks = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
+    want = _oracle_reference(oracle, steps)
+    ids = np.concatenate([r["id"] for r in ranks])
+    assert np.array_equal(np.sort(ids), np.arange(len(want["pos"]), dtype=np.uint32)), "every particle owned exactly once"
+    for d in ranks:
+        i = d["id"]
+        assert np.array_equal(d["hash"], want["hash"][i])
+        assert (np.abs(d["density"] - want["density"][i]) / want["density"][i]).max() < 1e-5
+        assert np.abs(d["pos"] - want["pos"][i]).max() < 2e-5
+        # exactly one general (all-to-all) step, at step 0; the cuts walked back towards balance one cell per check
+        assert int(d["general"]) == 1 and int(d["checks"]) == steps - 1 and int(d["moves"]) >= 2
+        inner_first, inner_now, inner_bal = d["first_cuts"][1:-1], d["cuts"][1:-1], d["balanced"][1:-1]
+        assert (np.abs(inner_now - inner_bal) < np.abs(inner_first - inner_bal)).all()
+        assert (np.abs(inner_now - inner_first) <= steps - 1).all()
+
+
 def _run(world, steps, rebalance_every=0, fast=False):
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, _free_port(), steps, rebalance_every, d, fast), nprocs=world, join=True)
