@@ -121,7 +121,9 @@ class ClockSampler:
     every 100 ms cost the sampled rank 0.9 ms per step of a 20-step region, every 20 ms from a separate
     process 5 ms per step). So: one sample when the region starts (before the first timed launch), one the
     moment it ends (the GPU is still at its load clocks), and in between only one every 0.5 s — a long region
-    is sampled throughout, a 25 ms one is not disturbed. nvidia-smi -lms as the fallback without the NVML binding."""
+    is sampled throughout, a 25 ms one is not disturbed. The after-effect of a query outlasts the call (the
+    stall shows up in the steps launched after it returned), so the first sample is taken before the warm-up
+    steps, not between them and the timed region. nvidia-smi -lms as the fallback without the NVML binding."""
     PERIOD_S = 0.5
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -138,6 +140,7 @@ class ClockSampler:
         self.max_mhz = None
         self._stop = threading.Event()
         self._thread = None
+        self.off = os.environ.get("SPH_CLOCK_SAMPLER") == "off"  # diagnostic runs only: no clocks key
         try:
             if os.environ.get("SPH_CLOCK_SAMPLER", "nvml") != "nvml":
                 raise ImportError("nvidia-smi sampler requested")
@@ -170,8 +173,13 @@ class ClockSampler:
             self._sample()
 
     def start(self):
+        """Call BEFORE the warm-up steps: the first sample is taken here, then 30 ms pass, so that its
+        after-effect on the GPU is over when the (untimed) warm-up steps bring the GPU back under load."""
+        if self.off:
+            return
         if self.nvml:
-            self._sample()  # region start (the launches that follow are not timed yet: events bracket the region)
+            self._sample()
+            time.sleep(0.03)
             self._thread = threading.Thread(target=self._loop, daemon=True)
             self._thread.start()
             return
@@ -188,6 +196,8 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.off:
+            return None
         if self.nvml:
             self._sample()  # the region has just ended: the GPU is still at its load clocks
             self._stop.set()
@@ -312,14 +322,14 @@ def run_single_gpu(args):
     settled = sim.download(S.ORDER_ID, fields=("pos", "vel"))
 
     warmup = max(args.warmup, 3)
+    clocks = ClockSampler(dev)
+    clocks.start()
     for _ in range(warmup):
         sim.step(1)
     sim.sync()
 
     # ---- the timed region: K steps through sph_step (the call a resident simulation makes: one captured
     # CUDA graph per step), one event pair per step on the library's stream, L2 flushed between steps ----
-    clocks = ClockSampler(dev)
-    clocks.start()
     launches0 = sim.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize(dev)

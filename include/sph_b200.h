@@ -117,8 +117,10 @@ const char *sph_last_error(const sph_handle *h);
 
 /* ---- state in / out -------------------------------------------------------------------- */
 
-/* Load n particles (n <= capacity). id may be NULL (ids become 0..n-1). Replaces the H2D copy of
- * src/kernels/sphGPU.cu:253-255. */
+/* Load n particles (n <= capacity). id may be NULL (ids become 0..n-1); given ids must be UNIQUE and below
+ * 2^31 (bit 31 marks a slab ghost row inside the library; an id with it set is refused with SPH_ERR_INVALID;
+ * uniqueness is the caller's contract: rows inside a cell are ordered by id, two equal ids in one cell would
+ * lose a row). Replaces the H2D copy of src/kernels/sphGPU.cu:253-255. */
 int sph_upload(sph_handle *h, uint64_t n, const float *host_pos_xyz, const float *host_vel_xyz,
                const uint32_t *host_id);
 /* Same, from device memory holding float4 rows (xyz + ignored w); ids 0..n-1. */

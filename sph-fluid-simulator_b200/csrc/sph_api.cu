@@ -73,7 +73,7 @@ struct sph_handle {
     int forces_cfg = 0, density_cfg = 0;
     // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
     // are in the cell order of the last build, i.e. from a slab force step until anything else touches them.
-    bool edge_scan_enabled = false;  // SPH_B200_EDGE_SCAN=1 (opt-in: see DESIGN.md §5 for the measurements)
+    bool edge_scan_enabled = true;   // SPH_B200_EDGE_SCAN=0 scans every row (see DESIGN.md §5 for the measurements)
     bool edge_ok = false;        // rows [0, n) are in the cell order h->cells describes
     bool edge_all = true;        // this step's scans look at every row
     uint64_t edge_sorted = 0;    // rows in cell order when this step began (arrivals are appended behind them)
@@ -723,6 +723,11 @@ int sph_upload(sph_handle *h, uint64_t n, const float *host_pos, const float *ho
     if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "upload of %llu particles exceeds capacity %llu",
                                 (unsigned long long)n, (unsigned long long)h->cap);
     if (n && (!host_pos || !host_vel)) return fail(h, SPH_ERR_INVALID, "pos/vel is NULL");
+    if (host_id)
+        for (uint64_t k = 0; k < n; ++k)
+            if (host_id[k] & W_GHOST)
+                return fail(h, SPH_ERR_INVALID, "id %u of row %llu has bit 31 set: ids must be unique and below 2^31", host_id[k],
+                            (unsigned long long)k);
     const size_t b3 = align_up(sizeof(float) * 3 * n, 256), b1 = align_up(sizeof(uint32_t) * n, 256);
     rc = ensure_scratch(h, 2 * b3 + b1 + 256);
     if (rc) return rc;

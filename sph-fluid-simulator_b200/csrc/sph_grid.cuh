@@ -158,6 +158,10 @@ __device__ __forceinline__ GridDesc plan_grid(const int *b, uint32_t max_cells, 
     for (int a = 0; a < 3; ++a) {
         long long ext = (long long)b[3 + a] + expand - lo[a] + 1;  // occupied cells on this axis
         if (ext < 1) ext = 1;                              // empty box (n == 0)
+        // A box saturated on two axes (positions at +/-inf or beyond 2^31 h after a blow-up: cell_of saturates)
+        // would overflow the 64-bit product below; 2^20 cells per axis is already far beyond any allocation,
+        // the halving loop takes it from there.
+        if (ext > (1LL << 20)) ext = 1LL << 20;
         dim[a] = ext + 2;
     }
     while (dim[0] * dim[1] * dim[2] > (long long)max_cells) {

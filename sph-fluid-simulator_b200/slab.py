@@ -703,16 +703,19 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sa
     del pos, vel, ids
     runner = SlabRunner(driver, s.dt, transport)
     runner.run(args.settle)
+    sim.sync()
+    # rank 0 samples its own GPU; one poller per job keeps NVML out of the other ranks' launch paths. The
+    # first sample is taken here, before the warm-up steps (see bench.ClockSampler: a query disturbs the
+    # launches that follow it).
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
     runner.run(warmup)
     sim.sync()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
-    # rank 0 samples its own GPU; one poller per job keeps NVML out of the other ranks' launch paths
-    clocks = ClockSampler(local) if rank == 0 else None
-    if clocks:
-        clocks.start()
     launches0 = sim.launch_count
     general0 = runner.general_steps
     stream = driver.e.stream

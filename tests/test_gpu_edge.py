@@ -113,6 +113,46 @@ np.savez(sys.argv[1], clamped=st.clamped, cells=st.grid_cells, **out)
     assert_fields_close(clipped, full, "clipped grid")
 
 
+def test_box_saturated_on_two_axes_is_clamped_not_overflowed(sph):
+    """Positions at +/-inf (or beyond 2^31 h) on two axes saturate getCell on both: the grid plan must clip
+    the box instead of overflowing its cell count, the outliers are clamped into the edge layer
+    and counted, and everybody else's results do not change."""
+    rng = np.random.default_rng(3)
+    s = sph.default_settings()
+    pos = rng.uniform([-2, 0.2, -2], [2, 2.5, 2], (4000, 3)).astype(np.float32)
+    vel = rng.normal(0, 0.3, pos.shape).astype(np.float32)
+    ids = np.arange(len(pos), dtype=np.uint32)
+    wild = pos.copy()
+    wild[0] = [np.inf, np.inf, 1.0]
+    wild[1] = [-3.0e38, 3.0e38, 0.5]
+    wild[2] = [3.0e38, 1.0, -np.inf]
+    outs = []
+    for p, keep in ((wild, slice(None)), (pos, slice(3, None))):
+        sim = sph.Sim(s, capacity=len(pos))
+        sim.upload(p[keep], vel[keep], ids[keep])
+        sim.step(2)
+        st = sim.stats()
+        d = sim.download(sph.ORDER_DEVICE)
+        outs.append((st, {k: v[np.argsort(d["id"])] for k, v in d.items()}))
+        sim.close()
+    (st_w, w), (st_c, c) = outs
+    assert st_w.nan_count >= 2 and st_c.nan_count == 0  # the +/-inf rows (3e38 is finite and gets mirrored by the walls)
+    assert 0 < st_w.grid_cells <= 1 << 30 and min(st_w.grid_dim) >= 3 and st_w.clamped >= 3
+    for k in ("pos", "vel", "force", "density"):
+        assert_bit_equal(w[k][3:], c[k], f"finite particles next to saturated outliers: {k}")
+
+
+def test_ids_with_the_ghost_bit_are_refused(sph):
+    """Bit 31 of an id is the library's ghost marker: such ids are refused at upload (ids must also be
+    unique — include/sph_b200.h — which is the caller's contract)."""
+    sim = sph.Sim(sph.default_settings(), capacity=8)
+    pos = np.full((2, 3), 0.5, np.float32)
+    with pytest.raises(sph.SphError) as e:
+        sim.upload(pos, np.zeros_like(pos), ids=np.array([1, 0x80000005], np.uint32))
+    assert e.value.code == 1  # SPH_ERR_INVALID
+    sim.close()
+
+
 def test_clump_takes_the_warp_cooperative_kernels(sph, oracle):
     """A clump (hundreds of neighbours per particle, what the reference's fluid collapses into after
     ~2000 steps) overflows the per-particle neighbour list and the per-run budget of the one-thread

@@ -118,12 +118,12 @@ def test_slab_step_is_bit_identical_to_single_gpu_gloo(sph, world, fast):
     _compare(ranks, want, world)
 
 
-@pytest.fixture
-def edge_scans():
-    """SPH_B200_EDGE_SCAN=1 for the spawned ranks: the sync-free steps look for migrants and ghosts in
-    the slab's edge x-layers only (opt-in)."""
+@pytest.fixture(params=["1", "0"], ids=["edge-scans", "full-scans"])
+def edge_scans(request):
+    """SPH_B200_EDGE_SCAN for the spawned ranks: 1 (the default) — the sync-free steps look for migrants and
+    ghosts in the slab's edge x-layers only; 0 — they look at every row. Same bits either way."""
     old = os.environ.get("SPH_B200_EDGE_SCAN")
-    os.environ["SPH_B200_EDGE_SCAN"] = "1"
+    os.environ["SPH_B200_EDGE_SCAN"] = request.param
     yield
     if old is None:
         del os.environ["SPH_B200_EDGE_SCAN"]
