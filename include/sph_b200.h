@@ -227,6 +227,28 @@ int sph_scene_block(int nx, int ny, int nz, float sep, float x0, float y0, float
 int sph_scene_block_slice(int nx, int ny, int nz, float sep, float x0, float y0, float z0, float h, unsigned seed,
                           int i0, int i1, float *host_pos_xyz, float *host_vel_xyz, uint32_t *host_ids);
 
+/* The same scenes generated ON THE DEVICE straight into the handle's state, bit-identical to the host
+ * generators above (the glibc rand() stream is reproduced by a polynomial jump of its linear recurrence, one
+ * chunk of the stream per thread): a 64 M-particle lattice takes milliseconds instead of seconds of serial
+ * rand() calls, and nothing crosses PCIe. Uses the handle's settings.h. Rows get the lattice ids
+ * i + (j + ny*k)*nx; sph_scene_block_device produces the rows with lattice x-index in [i0, i1) (one x-range
+ * per rank). Equivalent to generating on the host and calling sph_upload. */
+int sph_scene_cube_device(sph_handle *h, int width);
+int sph_scene_block_device(sph_handle *h, int nx, int ny, int nz, float sep, float x0, float y0, float z0, unsigned seed,
+                           int i0, int i1);
+
+/* Host-only self-test of the rand() jump-ahead behind the device generators (no CUDA call): the first
+ * ndraws outputs of glibc's rand() after srand(seed) against the stream rebuilt in chunks of chunk_draws from
+ * the jumped states; returns the number of mismatches (expected 0). */
+int sph_selftest_glibc_rand(unsigned seed, uint64_t ndraws, uint64_t chunk_draws, uint64_t *mismatches_out);
+
+/* Reset point: sph_set_reset_point keeps a device copy of the current rows; sph_reset restores it (device
+ * to device, no host traffic, no synchronisation) and rewinds the step count — what SPHSystem::reset
+ * (src/SPHSystem.cpp:136-139) and the GUI's R key (src/Tester.cpp:169-173) need, without regenerating and
+ * re-uploading the scene. */
+int sph_set_reset_point(sph_handle *h);
+int sph_reset(sph_handle *h);
+
 /* class SPHSystem (src/SPHSystem.h:24-57) for hosts that cannot include the C++ header
  * (sph-fluid-simulator_b200/host/SPHSystem.h): constructor, update, reset, startSimulation,
  * particleCount, and the renderer read-out that replaces `particles` / `sphereModelMtxs`.

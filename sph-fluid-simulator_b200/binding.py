@@ -103,6 +103,11 @@ def load_library() -> C.CDLL:
         "sph_stream": ([hp], C.c_void_p),
         "sph_scene_cube": ([C.c_int, C.c_float, fp, fp], C.c_int),
         "sph_scene_block": ([C.c_int] * 3 + [C.c_float] * 5 + [C.c_uint, fp, fp], C.c_int),
+        "sph_scene_cube_device": ([hp, C.c_int], C.c_int),
+        "sph_scene_block_device": ([hp] + [C.c_int] * 3 + [C.c_float] * 4 + [C.c_uint, C.c_int, C.c_int], C.c_int),
+        "sph_selftest_glibc_rand": ([C.c_uint, C.c_uint64, C.c_uint64, u64p], C.c_int),
+        "sph_set_reset_point": ([hp], C.c_int),
+        "sph_reset": ([hp], C.c_int),
         "sph_slab_enable": ([hp, C.c_int], C.c_int),
         "sph_slab_owned": ([hp], C.c_uint64),
         "sph_slab_count": ([hp, C.POINTER(C.c_int32), C.c_int, u64p], C.c_int),
@@ -263,6 +268,21 @@ class Sim:
         ids = None if ids is None else np.ascontiguousarray(ids, np.uint32)
         self._ck(self.lib.sph_upload(self._h, pos.shape[0], _ptr(pos, C.c_float), _ptr(vel, C.c_float),
                                      _ptr(ids, C.c_uint32)))
+
+    def scene_cube_device(self, width):
+        """initParticles on the device (bit-identical to scene_cube + upload)."""
+        self._ck(self.lib.sph_scene_cube_device(self._h, width))
+
+    def scene_block_device(self, nx, ny, nz, sep, origin, seed=1024, i0=0, i1=None):
+        """The dam-break block (rows with lattice x-index in [i0, i1)) generated on the device."""
+        self._ck(self.lib.sph_scene_block_device(self._h, nx, ny, nz, C.c_float(sep), C.c_float(origin[0]), C.c_float(origin[1]),
+                                                 C.c_float(origin[2]), seed, i0, nx if i1 is None else i1))
+
+    def set_reset_point(self):
+        self._ck(self.lib.sph_set_reset_point(self._h))
+
+    def reset(self):
+        self._ck(self.lib.sph_reset(self._h))
 
     def upload_device(self, n, dev_pos_ptr, dev_vel_ptr):
         self._ck(self.lib.sph_upload_device(self._h, n, C.c_void_p(dev_pos_ptr), C.c_void_p(dev_vel_ptr)))

@@ -19,6 +19,7 @@
 #include "sph_physics.cuh"
 #include "sph_io.cuh"
 #include "sph_slab.cuh"
+#include "sph_scene.cuh"
 
 using namespace sphb;
 
@@ -95,6 +96,11 @@ struct sph_handle {
 
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+
+    // Reset point: a device copy of the rows at the time of sph_set_reset_point (SPHSystem::reset, the GUI's R key)
+    float4 *reset_pos = nullptr, *reset_vel = nullptr;
+    uint64_t reset_n = 0;
+    bool have_reset = false;
 
     // Per-pass CUDA-event timing (the Timer blocks of src/sph.cpp:235,249,262): one event set per
     // timed step, drawn from a pool that grows on demand and is read back in sph_pass_times.
@@ -681,7 +687,7 @@ int sph_destroy(sph_handle *h)
     cudaFree(h->halo_rows[0]); cudaFree(h->halo_rows[1]); cudaFree(h->slab_counts);
     cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
-    cudaFree(h->stats_acc); cudaFree(h->scratch);
+    cudaFree(h->stats_acc); cudaFree(h->scratch); cudaFree(h->reset_pos); cudaFree(h->reset_vel);
     for (int k = 0; k < 2; ++k)
         if (h->peer_mailbox[k]) cudaIpcCloseMemHandle(h->peer_mailbox[k]);
     cudaFree(h->mailbox);
@@ -879,6 +885,183 @@ int sph_write_transforms(sph_handle *h, float *host_mat4)
     if (h->n) CK(cudaMemcpyAsync(host_mat4, h->scratch, 64 * h->n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return SPH_OK;
+}
+
+// ---- reset point and device-side scenes -----------------------------------------------------------
+
+int sph_set_reset_point(sph_handle *h)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (!h->have_state) return fail(h, SPH_ERR_STATE, "no particles uploaded");
+    if (!h->reset_pos) {
+        CK(cudaMalloc(&h->reset_pos, sizeof(float4) * h->cap));
+        CK(cudaMalloc(&h->reset_vel, sizeof(float4) * h->cap));
+    }
+    if (h->n) {
+        CK(cudaMemcpyAsync(h->reset_pos, h->pos[h->cur], sizeof(float4) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->reset_vel, h->vel[h->cur], sizeof(float4) * h->n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->reset_n = h->n;
+    h->have_reset = true;
+    return SPH_OK;
+}
+
+int sph_reset(sph_handle *h)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (!h->have_reset) return fail(h, SPH_ERR_STATE, "no reset point: call sph_set_reset_point after loading the initial state");
+    if (h->reset_n) {
+        CK(cudaMemcpyAsync(h->pos[h->cur], h->reset_pos, sizeof(float4) * h->reset_n, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->vel[h->cur], h->reset_vel, sizeof(float4) * h->reset_n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return after_upload(h, h->reset_n);  // rows, step count, bounding box: as after an upload (no host traffic, no sync)
+}
+
+namespace {
+
+// glibc's rand() after srand(seed) as a linear recurrence (sph_scene.cuh): r[i] = r[i-31] + r[i-3] mod 2^32,
+// output k = r[k + 344] >> 1. seed_state fills r[0..30] the way __srandom_r does.
+void glibc_seed_state(unsigned seed, uint32_t r[31])
+{
+    int32_t word = seed ? (int32_t)seed : 1;
+    r[0] = (uint32_t)word;
+    for (int i = 1; i < 31; ++i) {
+        const long hi = word / 127773, lo = word % 127773;
+        long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        word = (int32_t)w;
+        r[i] = (uint32_t)word;
+    }
+}
+
+// c = a * b mod (x^31 - x^28 - 1), coefficients mod 2^32.
+void poly_mulmod(const uint32_t a[31], const uint32_t b[31], uint32_t c[31])
+{
+    uint32_t t[61] = {0};
+    for (int i = 0; i < 31; ++i)
+        for (int j = 0; j < 31; ++j) t[i + j] += a[i] * b[j];
+    for (int k = 60; k >= 31; --k) {  // x^k = x^(k-3) + x^(k-31)
+        t[k - 3] += t[k];
+        t[k - 31] += t[k];
+    }
+    std::memcpy(c, t, sizeof(uint32_t) * 31);
+}
+
+// For every chunk q (chunk_draws outputs each, nchunks of them): the 31 words r[m .. m+30] with
+// m = q * chunk_draws + 344 - 31, i.e. the window from which output q * chunk_draws is the next one produced.
+void glibc_rand_jump(unsigned seed, uint64_t chunk_draws, uint64_t nchunks, std::vector<uint32_t> &out)
+{
+    out.resize(nchunks * 31);
+    uint32_t r[31 + 344];
+    glibc_seed_state(seed, r);
+    for (int i = 31; i < 34; ++i) r[i] = r[i - 31];  // glibc copies the first three words, the recurrence starts at 34
+    for (int i = 34; i < 31 + 344; ++i) r[i] = r[i - 31] + r[i - 3];
+    // x^chunk_draws mod p by square and multiply
+    uint32_t A[31] = {0}, base[31] = {0}, tmp[31];
+    A[0] = 1;
+    base[1] = 1;
+    for (uint64_t e = chunk_draws; e; e >>= 1) {
+        if (e & 1) { poly_mulmod(A, base, tmp); std::memcpy(A, tmp, sizeof tmp); }
+        poly_mulmod(base, base, tmp);
+        std::memcpy(base, tmp, sizeof tmp);
+    }
+    uint32_t win[61];
+    std::memcpy(win, r + 344 - 31, sizeof(uint32_t) * 31);  // chunk 0
+    for (uint64_t q = 0; q < nchunks; ++q) {
+        std::memcpy(&out[q * 31], win, sizeof(uint32_t) * 31);
+        if (q + 1 == nchunks) break;
+        for (int i = 31; i < 61; ++i) win[i] = win[i - 31] + win[i - 3];
+        uint32_t next[31];
+        for (int j = 0; j < 31; ++j) {  // r[m + C + j] = sum_k A_k r[m + k + j]
+            uint32_t acc = 0;
+            for (int k = 0; k < 31; ++k) acc += A[k] * win[k + j];
+            next[j] = acc;
+        }
+        std::memcpy(win, next, sizeof next);
+    }
+}
+
+int scene_device(sph_handle *h, const SceneDesc &d, unsigned seed)
+{
+    int rc = enter_exact(h);
+    if (rc) return rc;
+    if (d.nx < 0 || d.ny < 0 || d.nz < 0 || d.i0 < 0 || d.i1 < d.i0 || d.i1 > d.nx) return fail(h, SPH_ERR_INVALID, "bad lattice / x-range");
+    const uint64_t n_total = (uint64_t)d.nx * d.ny * d.nz, n = (uint64_t)(d.i1 - d.i0) * d.ny * d.nz;
+    if (n_total >= (1ull << 31)) return fail(h, SPH_ERR_INVALID, "lattice of %llu particles: ids must stay below 2^31", (unsigned long long)n_total);
+    if (n > h->cap) return fail(h, SPH_ERR_CAPACITY, "%llu particles exceed capacity %llu", (unsigned long long)n, (unsigned long long)h->cap);
+    if (n_total) {
+        // only the chunks up to the last produced row are needed (draws are consumed x-outer)
+        const uint64_t last = (uint64_t)d.i1 * d.ny * d.nz;
+        const uint64_t nchunks = (last + SCENE_CHUNK - 1) / SCENE_CHUNK;
+        std::vector<uint32_t> st;
+        glibc_rand_jump(seed, 3ull * SCENE_CHUNK, nchunks, st);
+        rc = ensure_scratch(h, st.size() * sizeof(uint32_t) + 256);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->scratch, st.data(), st.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        k_scene_block<<<blocks_for(nchunks, SCENE_THREADS), SCENE_THREADS, 0, h->stream>>>((const uint32_t *)h->scratch, last, d,
+                                                                                          h->pos[h->cur], h->vel[h->cur]);
+        CK_LAUNCH();
+        CK(cudaStreamSynchronize(h->stream));  // st goes out of scope
+    }
+    return after_upload(h, n);
+}
+
+}  // namespace
+
+// Host-only self-test of the jump-ahead (no CUDA call): the first `ndraws` outputs of glibc's rand() after
+// srand(seed) against the same stream rebuilt chunk by chunk from the jumped states.
+int sph_selftest_glibc_rand(unsigned seed, uint64_t ndraws, uint64_t chunk_draws, uint64_t *mismatches_out)
+{
+    if (!mismatches_out || chunk_draws == 0 || ndraws == 0 || ndraws > (1ull << 30)) return SPH_ERR_INVALID;
+    const uint64_t nchunks = (ndraws + chunk_draws - 1) / chunk_draws;
+    std::vector<uint32_t> st;
+    glibc_rand_jump(seed, chunk_draws, nchunks, st);
+    std::srand(seed);
+    uint64_t bad = 0;
+    for (uint64_t q = 0; q < nchunks; ++q) {
+        uint32_t w[31];
+        std::memcpy(w, &st[q * 31], sizeof w);
+        int p = 0;
+        const uint64_t m = std::min(chunk_draws, ndraws - q * chunk_draws);
+        for (uint64_t t = 0; t < m; ++t) {
+            const uint32_t r = w[p] + w[(p + 28) % 31];
+            w[p] = r;
+            p = (p + 1) % 31;
+            bad += (uint32_t)std::rand() != (r >> 1);
+        }
+    }
+    *mismatches_out = bad;
+    return SPH_OK;
+}
+
+int sph_scene_cube_device(sph_handle *h, int width)
+{
+    if (!h) return SPH_ERR_INVALID;
+    SceneDesc d{};
+    d.nx = d.ny = d.nz = width;
+    d.i0 = 0;
+    d.i1 = width;
+    d.h = h->settings.h;
+    d.sep = d.h + 0.01f;  // src/SPHSystem.cpp:80
+    d.x0 = d.z0 = -1.5f;
+    d.y0 = d.h;           // "+ h + 0.1f" (src/SPHSystem.cpp:94): two additions, in this order
+    d.y1 = 0.1f;
+    d.cube = 1;
+    return scene_device(h, d, 1024u);
+}
+
+int sph_scene_block_device(sph_handle *h, int nx, int ny, int nz, float sep, float x0, float y0, float z0, unsigned seed,
+                           int i0, int i1)
+{
+    if (!h) return SPH_ERR_INVALID;
+    SceneDesc d{};
+    d.nx = nx; d.ny = ny; d.nz = nz;
+    d.i0 = i0; d.i1 = i1;
+    d.h = h->settings.h;
+    d.sep = sep; d.x0 = x0; d.y0 = y0; d.z0 = z0;
+    return scene_device(h, d, seed);
 }
 
 // ---- the step ---------------------------------------------------------------------------------

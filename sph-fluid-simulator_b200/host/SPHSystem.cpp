@@ -132,9 +132,10 @@ SPHSystem::~SPHSystem()
 
 void SPHSystem::initParticles()
 {
-    std::vector<float> pos(3 * particleCount), vel(3 * particleCount);
-    sceneCube(particleCubeWidth, settings.h, pos.data(), vel.data());
-    check(sph_upload(handle_, particleCount, pos.data(), vel.data(), nullptr), handle_, "sph_upload");
+    // The cube of src/SPHSystem.cpp:76-108, generated on the device (bit-identical to sceneCube: the tests
+    // compare the two), and kept as the reset point so that reset() is a device-to-device copy.
+    check(sph_scene_cube_device(handle_, (int)particleCubeWidth), handle_, "sph_scene_cube_device");
+    check(sph_set_reset_point(handle_), handle_, "sph_set_reset_point");
 }
 
 void SPHSystem::update(float deltaTime)
@@ -147,7 +148,7 @@ void SPHSystem::update(float deltaTime)
 
 void SPHSystem::reset()
 {
-    initParticles();
+    check(sph_reset(handle_), handle_, "sph_reset");  // src/SPHSystem.cpp:136-139 without the host loop and the upload
     started_ = false;
 }
 

@@ -696,11 +696,11 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sa
 
     per = nx // world
     i0, i1 = rank * per, (rank + 1) * per if rank < world - 1 else nx
-    pos, vel, ids = S.scene_block_slice(nx, ny, nz, scene["sep"], scene["origin"], scene["h"], scene["seed"], i0, i1)
-    n_local, n_total = pos.shape[0], nx * ny * nz
+    n_local, n_total = (i1 - i0) * ny * nz, nx * ny * nz
     driver, sim = make_gpu_driver(s, int(n_local * 1.5) + (1 << 20), local, rank, world)
-    sim.upload(pos, vel, ids)
-    del pos, vel, ids
+    # this rank's x-range of the lattice, generated on its GPU (bit-identical to the host generator, whose
+    # serial rand() loop over the whole 64 M lattice costs every rank seconds)
+    sim.scene_block_device(nx, ny, nz, scene["sep"], scene["origin"], scene["seed"], i0, i1)
     runner = SlabRunner(driver, s.dt, transport)
     runner.run(args.settle)
     sim.sync()
@@ -853,11 +853,9 @@ def single_gpu_base(S, args, scene_fn, s, local, warmup):
     replay, as a single-GPU user would run it): settle, warm up, then `steps` steps between two events."""
     b = scene_fn(1)
     bx, by, bz = b["dims"]
-    pos, vel = S.scene_block(bx, by, bz, b["sep"], b["origin"], b["h"], b["seed"])
-    n = pos.shape[0]
+    n = bx * by * bz
     sim = S.Sim(s, capacity=n, device=local)
-    sim.upload(pos, vel)
-    del pos, vel
+    sim.scene_block_device(bx, by, bz, b["sep"], b["origin"], b["seed"])
     sim.step(args.settle + warmup)
     sim.sync()
     stream = torch.cuda.ExternalStream(sim.stream, device=torch.device("cuda", local))

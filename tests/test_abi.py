@@ -76,6 +76,17 @@ def test_scene_block_matches_oracle_generator(sph, oracle):
     assert sph.scene_block(0, 3, 3, 0.1, (0, 0, 0), 0.1)[0].shape == (0, 3)
 
 
+def test_rand_jump_ahead_reproduces_glibc_rand(sph):
+    """The device scene generators rebuild glibc's rand() stream chunk by chunk from jumped states
+    (x^n mod x^31 - x^28 - 1 over Z/2^32); this host-only self-test compares with rand() itself."""
+    lib = sph.load_library()
+    for seed, ndraws, chunk in ((1024, 2_000_000, 3072), (1, 50_000, 7), (0, 10_000, 1000), (4_000_000_000, 20_000, 31),
+                                (99, 400_000, 3 * 4096)):
+        bad = ctypes.c_uint64(1)
+        assert lib.sph_selftest_glibc_rand(seed, ndraws, chunk, ctypes.byref(bad)) == 0
+        assert bad.value == 0, (seed, ndraws, chunk, bad.value)
+
+
 def test_no_fallback_without_a_gpu(sph):
     import torch
     if torch.cuda.is_available():
