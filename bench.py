@@ -513,6 +513,7 @@ def cpu_sample_for(args):
 def run_multi_gpu(args):
     slab = __import__("importlib").import_module("sph-fluid-simulator_b200.slab")
     scene_fn = dam_break_16m if args.workload == "dam-break-16M" else weak_scaling_block
+    args.strong_scene = dam_break_16m(args.gpus)  # carried as a sub-record of the weak-scaling lines
     slab.bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sample_for(args))
 
 
@@ -532,6 +533,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak-base", action="store_true", help="skip the single-GPU run of the weak-scaling per-GPU workload")
     ap.add_argument("--no-slab-parity", action="store_true", help="skip the cross-GPU bit-parity check of the N>1 lines")
+    ap.add_argument("--no-strong-subrecord", action="store_true", help="skip the config-2 (16 M, strong scaling) sub-record of the N>1 lines")
     ap.add_argument("--multi-cpu-budget-s", type=float, default=25.0, help="CPU seconds for the cpu_baseline of an N>1 line")
     ap.add_argument("--workload", default="auto", choices=["auto", "dam-break-1M", "weak", "dam-break-16M"],
                     help="auto: config 1 at N=1, config 3 (weak scaling, 8 M particles per GPU) at N>1; "

@@ -769,11 +769,11 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sa
             return int(cnt.value)
 
         m = read_back()
-        k_e2e = max(2, min(args.e2e_steps, 5))
+        k_e2e = max(2, min(args.e2e_steps, 8))
         t_e2e = 0.0
         iter_ms = []
         import time
-        e2e_warm = 2  # untimed iterations: first-touch of the pinned buffers, lazy transport set-up
+        e2e_warm = 3  # untimed iterations: first-touch of the pinned buffers, lazy transport set-up
         for k in range(k_e2e + e2e_warm):
             if world > 1:
                 dist.barrier()
@@ -799,6 +799,15 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sa
                        "sph_slab_download_owned(pos, vel, id into pinned host memory)"}
     total_s = float(ms.item()) * 1e-3
     value = n_total * args.steps / total_s
+
+    # Config 2 (16 M dam break, strong scaling) as a sub-record, when this line is the weak-scaling one.
+    strong = None
+    strong_scene = getattr(args, "strong_scene", None)
+    if strong_scene is not None and scene.get("scaling", "weak") == "weak" and not getattr(args, "no_strong_subrecord", False):
+        sim.close()  # free this rank's 8 M-particle state first (driver / runner are only read for their counters below)
+        torch.cuda.empty_cache()
+        strong = strong_scaling_subrecord(S, args, strong_scene, local, rank, world, transport, warmup)
+
     if rank == 0:
         peak, peak_src = peaks()
         if base:
@@ -832,6 +841,7 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sa
                        "single_gpu_same_workload": base,
                        "scaling_efficiency_vs_same_workload": (value / world / base["value"]) if base else None,
                        "slab_parity": parity,
+                       "strong_scaling_16M": strong,
                        "rank0_mean_density": st.mean_density, "rank0_grid_dim": list(st.grid_dim),
                        "phase_ms_per_step": phases},
             "clocks": clk,
@@ -846,6 +856,47 @@ def bench_weak_scaling(args, scene_fn, METRIC, UNIT, ClockSampler, peaks, cpu_sa
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def strong_scaling_subrecord(S, args, scene, local, rank, world, transport, warmup):
+    """Config 2 (the 16 M dam break, the same field whatever the number of GPUs) through the same slab runner,
+    timed the same way, as a sub-record of the N > 1 lines: strong scaling, so that it reaches a driver box."""
+    s = S.scaled_settings(scene["h"])
+    nx, ny, nz = scene["dims"]
+    per = nx // world
+    i0, i1 = rank * per, (rank + 1) * per if rank < world - 1 else nx
+    n_local, n_total = (i1 - i0) * ny * nz, nx * ny * nz
+    driver, sim = make_gpu_driver(s, int(n_local * 1.6) + (1 << 20), local, rank, world)
+    sim.scene_block_device(nx, ny, nz, scene["sep"], scene["origin"], scene["seed"], i0, i1)
+    runner = SlabRunner(driver, s.dt, transport, check_every=100)
+    runner.run(args.settle + warmup)
+    sim.sync()
+    if world > 1:
+        dist.barrier()
+    stream = driver.e.stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    general0 = runner.general_steps
+    e0.record(stream)
+    runner.run(args.steps)
+    e1.record(stream)
+    sim.sync()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
+    owned = torch.tensor([int(sim.stats().count)], dtype=torch.int64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        owned_all = [torch.zeros_like(owned) for _ in range(world)]
+        dist.all_gather(owned_all, owned)
+        owned_list = [int(o.item()) for o in owned_all]
+    else:
+        owned_list = [int(owned.item())]
+    sim.close()
+    torch.cuda.empty_cache()
+    t = float(ms.item()) * 1e-3
+    return {"workload": scene["name"], "scaling": "strong", "particles": n_total, "particles_per_gpu": owned_list,
+            "h": scene["h"], "dt": s.dt, "lattice": [nx, ny, nz], "settle_steps": args.settle, "steps": args.steps,
+            "ms_per_step": 1e3 * t / args.steps, "value": n_total * args.steps / t,
+            "general_steps_in_timed_region": runner.general_steps - general0, "cut_moves": runner.cut_moves,
+            "imbalance_at_last_check": driver.last_imbalance}
 
 
 def single_gpu_base(S, args, scene_fn, s, local, warmup):
