@@ -79,6 +79,7 @@ struct sph_handle {
     bool edge_all = true;        // this step's scans look at every row
     uint64_t edge_sorted = 0;    // rows in cell order when this step began (arrivals are appended behind them)
     bool tile_armed = false;  // k_forces_tile's dynamic shared memory limit has been raised
+    bool tma_armed = false;   // ... and k_density_tma's
     unsigned long long *slab_counts = nullptr;  // SLAB_MAX_RANKS counters + cursors
     uint32_t *cells = nullptr;
     uint32_t max_cells = 0;
@@ -322,7 +323,19 @@ int launch_density(sph_handle *h, uint32_t n)
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->ctr)
     int cfg = h->density_cfg;
-    if (cfg < 10 && (uint64_t)(NLIST_ROWS + 1) * h->cap >= (1ull << 32)) cfg = 10;
+    if ((cfg < 10 || cfg >= 50) && (uint64_t)(NLIST_ROWS + 1) * h->cap >= (1ull << 32)) cfg = 10;
+    if (cfg >= 50) {
+        // TMA-staged neighbourhoods (measured alternative): persistent blocks, 3 per SM at 58 KB each
+        auto kern = cfg == 51 ? k_density_tma<4> : k_density_tma<2>;
+        if (!h->tma_armed) {
+            CK(cudaFuncSetAttribute(k_density_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaTile)));
+            CK(cudaFuncSetAttribute(k_density_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TmaTile)));
+            h->tma_armed = true;
+        }
+        const unsigned tiles = blocks_for(n, PHYS_THREADS);
+        kern<<<std::min(tiles, (unsigned)h->num_sms * 3u), PHYS_THREADS, sizeof(TmaTile), s>>>(
+            h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
+    } else
     switch (cfg) {
     case 1: LAUNCH_S(12, 4); break;
     case 2: LAUNCH_S(10, 2); break;

@@ -297,6 +297,42 @@ def test_device_scene_generators_and_reset_point(sph):
     sim.close()
 
 
+def test_density_kernel_variants_return_the_same_bits():
+    """SPH_B200_DENSITY_CFG: 0 = staged row walk (default), 10 = the round-1 kernel, 50 = the TMA-staged walk
+    (neighbourhoods brought into shared memory by cp.async.bulk under an mbarrier, double-buffered; kept as a
+    measured alternative). Same neighbour lists in the same order, the same sequence of rounded
+    additions: same bits, on a dense cube with hash-collision cells and on a state with a clump."""
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import sph_b200 as S
+from conftest import load_golden
+g = load_golden("cube20_step200.npz")
+out = {}
+sim = S.Sim(S.default_settings(), capacity=len(g["pos0"])); sim.upload(g["pos0"], g["vel0"]); sim.step(5)
+out.update({"a_" + k: v for k, v in sim.download(S.ORDER_ID).items()})
+rng = np.random.default_rng(5)
+d = rng.normal(size=(1500, 3)); d *= (0.25 * rng.uniform(0, 1, (1500, 1)) ** (1 / 3)) / np.linalg.norm(d, axis=1, keepdims=True)
+pos = np.concatenate([d + [1.0, 1.0, 1.0], rng.uniform([-3, 0.2, -3], [3, 3, 3], (2500, 3))]).astype(np.float32)
+sim.upload(pos, np.zeros_like(pos)); sim.step(2)
+out.update({"b_" + k: v for k, v in sim.download(S.ORDER_ID).items()})
+np.savez(sys.argv[1], **out)
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        outs = {}
+        for cfg in ("0", "10", "50"):
+            env = dict(os.environ)
+            env["SPH_B200_DENSITY_CFG"] = cfg
+            f = os.path.join(d, f"d{cfg}.npz")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=env)
+            outs[cfg] = dict(np.load(f))
+    for cfg in ("10", "50"):
+        for k in outs["0"]:
+            if k.split("_")[1] in ("pos", "vel", "force", "density"):
+                assert_bit_equal(outs[cfg][k], outs["0"][k], f"density cfg {cfg} vs default: {k}")
+
+
 def test_errors_are_reported_not_thrown(sph):
     s = sph.default_settings()
     sim = sph.Sim(s, capacity=10)
