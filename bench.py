@@ -301,6 +301,58 @@ def work_model(candidates_mean, neighbours_mean):
             "step": 18.0 * candidates_mean + 51.0 * neighbours_mean}
 
 
+def other_configs(S, torch, dev, peak):
+    """BASELINE.json configs 0 and 4 as sub-records of the N = 1 line (so that they reach a driver box):
+    the shipped default cube (launch-bound: one captured graph per step) and neighbour search only
+    (hash + counting sort by cell + cell ranges) on uniform-random fields, 128 B/particle algorithmic."""
+    out = {}
+    s = S.default_settings()
+    sim = S.Sim(s, capacity=3375, device=dev)
+    sim.scene_cube_device(15)  # src/Tester.cpp:90-91: SPHSystem(15, SPHSettings(0.02, 1000, 1, 1.04, 0.15, -9.8, 0.2))
+    sim.step(300)
+    sim.sync()
+    t0 = time.perf_counter()
+    sim.step(3000)
+    sim.sync()
+    dt = time.perf_counter() - t0
+    st = sim.stats()
+    out["config0_default_cube"] = {"particles": 3375, "steps": 3000, "steps_per_second": 3000 / dt, "us_per_step": 1e6 * dt / 3000,
+                                   "value": 3375 * 3000 / dt, "unit": UNIT, "mean_density": st.mean_density,
+                                   "call": "sph_step(h, 0.003, 3000): captured CUDA graphs of 16 steps, wall clock incl. launches"}
+    sim.close()
+    rows = []
+    for m in (1, 16, 100):
+        n = m * 1000000
+        h = float((4096.0 * 4.0 / n) ** (1.0 / 3.0))  # ~4 particles per cell in the 16 x 16 x 16 box
+        g = torch.Generator(device=f"cuda:{dev}")
+        g.manual_seed(1024)
+        lo = torch.tensor([h - 8, h, h - 8], device=f"cuda:{dev}")
+        hi = torch.tensor([8 - h, 16.0, 8 - h], device=f"cuda:{dev}")
+        p4 = torch.zeros((n, 4), dtype=torch.float32, device=f"cuda:{dev}")
+        p4[:, :3] = lo + (hi - lo) * torch.rand((n, 3), generator=g, device=f"cuda:{dev}")
+        v4 = torch.zeros((n, 4), dtype=torch.float32, device=f"cuda:{dev}")
+        torch.cuda.synchronize(dev)
+        sim = S.Sim(S.scaled_settings(h), capacity=n, device=dev)
+        sim.upload_device(n, p4.data_ptr(), v4.data_ptr())
+        del p4, v4
+        sim.neighbor_search(3)
+        sim.sync()
+        stream = torch.cuda.ExternalStream(sim.stream, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        sim.neighbor_search(10)
+        e1.record(stream)
+        sim.sync()
+        ms = e0.elapsed_time(e1) / 10
+        rows.append({"particles": n, "h": h, "grid_cells": int(sim.stats().grid_cells), "ms": ms, "particles_per_s": n / (ms * 1e-3),
+                     "algorithmic_gbs": 128.0 * n / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": 128.0 * n / (ms * 1e-3) / 1e9 / peak})
+        sim.close()
+        torch.cuda.empty_cache()
+    out["config4_neighbour_search_only"] = {"field": "uniform random in the box, ~4 particles per cell, device-generated (seed 1024)",
+                                            "call": "sph_neighbor_search(h, 10): 5 kernels per build", "sizes": rows}
+    return out
+
+
 def run_single_gpu(args):
     import torch
     import sph_b200 as S
@@ -449,6 +501,8 @@ def run_single_gpu(args):
         weak_base = slab.single_gpu_base(S, args, weak_scaling_block, s3, dev, warmup)
         weak_base["step_hbm_frac"] = weak_base["step_achieved_gbs"] / peak
 
+    others = None if args.no_other_configs else other_configs(S, torch, dev, peak)
+
     # ---- CPU baseline on a bounded sample: the same settled state, a few full-size steps ----
     cpu = None
     if not args.no_cpu_baseline:
@@ -489,6 +543,7 @@ def run_single_gpu(args):
                    "ms_per_step_p50": float(np.median(step_ms)), "ms_per_step_max": float(step_ms.max()),
                    "timed_call": "sph_step(h, dt, 1) per step: one captured CUDA graph (9 kernels) replayed per call",
                    "weak_scaling_base": weak_base,
+                   "other_configs": others,
                    "reference_cuda_baseline": ref_cuda},
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 60 * n, "d2h_bytes_per_step": 124 * n,
@@ -532,6 +587,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak-base", action="store_true", help="skip the single-GPU run of the weak-scaling per-GPU workload")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config-0 / config-4 sub-records of the N=1 line")
     ap.add_argument("--no-slab-parity", action="store_true", help="skip the cross-GPU bit-parity check of the N>1 lines")
     ap.add_argument("--no-strong-subrecord", action="store_true", help="skip the config-2 (16 M, strong scaling) sub-record of the N>1 lines")
     ap.add_argument("--multi-cpu-budget-s", type=float, default=25.0, help="CPU seconds for the cpu_baseline of an N>1 line")
