@@ -70,6 +70,11 @@ struct sph_handle {
     P2PLayout p2p{};
     uint64_t p2p_H = 0, p2p_M = 0;
     uint32_t p2p_epoch = 0;
+    int slab_lo = 0, slab_hi = 0;  // this rank's x-cell range in the current sync-free step (0, 0: unknown -> no interior range)
+    cudaStream_t stream2 = nullptr;  // peer steps: the density exchange runs here, next to the interior rows' force pass
+    cudaEvent_t ev_dens = nullptr, ev_rho = nullptr;
+    bool p2p_overlap = true;       // SPH_B200_P2P_OVERLAP=0: everything on one stream, one force launch
+    bool rho_pending = false;      // ev_rho has been recorded for this step's force pass to wait on
     bool p2p_clean = false;   // the peer step's device cursors / done-counters are zero (it re-zeroes them itself)
     int forces_cfg = 0, density_cfg = 0;
     // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
@@ -279,7 +284,7 @@ int build_grid(sph_handle *h)
                                                             &h->ctr->ticket, &h->ctr->epoch);
     CK_STEP_LAUNCH();
     k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot, h->gd,
-                                                                   h->slab_mode ? h->ctr : nullptr);
+                                                                   h->slab_mode ? h->ctr : nullptr, h->slab_lo, h->slab_hi);
     CK_STEP_LAUNCH();
     uint32_t n_sorted = n;
     const uint32_t *n_dev = nullptr;
@@ -359,7 +364,7 @@ int launch_density(sph_handle *h, uint32_t n)
 // column), FI_STEP_WRITE_FORCE (the stateless drop-in call fills Particle::force every step) or
 // FI_FORCE_ONLY (recompute the force column of the last step on demand; start-of-step rows are in
 // the other buffers). SPH_B200_FORCES_CFG selects launch shapes for experiments.
-int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
+int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int part = 0)
 {
     cudaStream_t s = h->stream;
     // FI_FORCE_ONLY reads the start-of-step rows, which after the step live in the non-current buffers
@@ -367,7 +372,7 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
 #define LAUNCH_FI(T, B, M)                                                                                       \
     k_forces_integrate<T, B, M><<<blocks_for(n, T), T, 0, s>>>(                                                   \
         h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt,              \
-        h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map)
+        h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part)
 #define LAUNCH_FH(M)                                                                                              \
     k_forces_heavy<M><<<h->num_sms * 4, HEAVY_THREADS, 0, s>>>(h->pos[in], h->vel[in], h->gd, h->cells, h->P, dt,  \
                                                               h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr,   \
@@ -389,8 +394,13 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
                                                     h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1], h->vel[in ^ 1], \
                                                     h->force, h->ctr, h->parity ^ 1, h->map);                     \
     } while (0)
-        switch (h->forces_cfg) {
+        switch ((part != 0 && h->forces_cfg == 6) ? 2 : h->forces_cfg) {  // the tile-staged variant has no split form
         case 6: LAUNCH_FT(128, 5, 1408); break;  // shared-memory staged neighbourhoods: measured 2-4x slower
+        case 7:  // the scalar form of the force terms (A/B against the packed default: same bits)
+            k_forces_integrate<128, 10, FI_STEP, false><<<blocks_for(n, 128), 128, 0, s>>>(
+                h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1],
+                h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part);
+            break;
         case 1: LAUNCH_FI(128, 8, FI_STEP); break;
         case 3: LAUNCH_FI(64, 16, FI_STEP); break;
         case 4: LAUNCH_FI(256, 4, FI_STEP); break;
@@ -400,6 +410,7 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode)
     }
 #undef LAUNCH_FI
     CK_STEP_LAUNCH();
+    if (part == 1) return SPH_OK;  // the rows outside the interior range follow in a second launch, which completes the pass
     if (mode == FI_FORCE_ONLY) LAUNCH_FH(FI_FORCE_ONLY);
     else if (mode == FI_STEP_WRITE_FORCE) LAUNCH_FH(FI_STEP_WRITE_FORCE);
     else LAUNCH_FH(FI_STEP);
@@ -535,7 +546,7 @@ int build_hash16_order(sph_handle *h, bool need_map)
     CK_LAUNCH();
     if (need_map && n) {
         k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->h16_cells,
-                                                                   h->slot, nullptr, nullptr);
+                                                                   h->slot, nullptr, nullptr, 0, 0);
         CK_LAUNCH();
         k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot, h->cell_rank, n, h->h16_cells,
                                                                           h->map, nullptr);
@@ -682,6 +693,10 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaHostAlloc(&nh->pinned_rows, 2 * sizeof(uint32_t), cudaHostAllocDefault));
     nh->pinned_rows[0] = nh->pinned_rows[1] = 0;
     CKC(cudaEventCreateWithFlags(&nh->ev_rows, cudaEventDisableTiming));
+    CKC(cudaStreamCreateWithFlags(&nh->stream2, cudaStreamNonBlocking));
+    CKC(cudaEventCreateWithFlags(&nh->ev_dens, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&nh->ev_rho, cudaEventDisableTiming));
+    if (const char *e = std::getenv("SPH_B200_P2P_OVERLAP")) nh->p2p_overlap = std::atoi(e) != 0;
     const uint32_t c65536 = 65536u;
     CKC(cudaMemcpyAsync(nh->const_65536, &c65536, sizeof c65536, cudaMemcpyHostToDevice, nh->stream));
     CKC(cudaStreamSynchronize(nh->stream));
@@ -707,6 +722,9 @@ int sph_destroy(sph_handle *h)
     drop_graphs(h);
     if (h->pinned_rows) cudaFreeHost(h->pinned_rows);
     if (h->ev_rows) cudaEventDestroy(h->ev_rows);
+    if (h->ev_dens) cudaEventDestroy(h->ev_dens);
+    if (h->ev_rho) cudaEventDestroy(h->ev_rho);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     for (auto &pe : h->ev_pool)
         for (auto &e : pe.e) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1472,6 +1490,7 @@ int sph_slab_pack(sph_handle *h, const int32_t *cuts, int world, int self, void 
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
     h->slab_fast = false;
+    h->slab_lo = h->slab_hi = 0;
     h->edge_ok = false;
     return SPH_OK;
 }
@@ -1591,7 +1610,16 @@ int sph_slab_step_forces(sph_handle *h, float dt)
     if (!(dt > 0.f)) dt = h->settings.dt;
     const uint32_t n = (uint32_t)h->n;
     if (n) {
-        rc = launch_forces_integrate(h, n, dt, FI_STEP);
+        if (h->rho_pending) {
+            // the halo densities are still on their way (second stream): rows without ghost neighbours first
+            rc = launch_forces_integrate(h, n, dt, FI_STEP, 1);
+            if (rc) return rc;
+            CK(cudaStreamWaitEvent(h->stream, h->ev_rho, 0));
+            h->rho_pending = false;
+            rc = launch_forces_integrate(h, n, dt, FI_STEP, 2);
+        } else {
+            rc = launch_forces_integrate(h, n, dt, FI_STEP);
+        }
         if (rc) return rc;
         h->parity ^= 1;  // the integration accumulated the next step's box into the other slot
         h->have_bbox_from_integration = true;
@@ -1701,6 +1729,7 @@ int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, 
     h->n_ghost = 0;
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
+    h->slab_lo = h->slab_hi = 0;
     ++h->launches;
     return SPH_OK;
 }
@@ -1900,6 +1929,9 @@ int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, i
     h->n_ghost = 0;
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
+    // the x-layers of this slab that touch a neighbour's ghosts: lo (if there is a left neighbour), hi - 1 (right)
+    h->slab_lo = dst[0] ? lo : -0x3fffffff;
+    h->slab_hi = dst[1] ? hi : 0x3fffffff;
     return SPH_OK;
 }
 
@@ -1992,11 +2024,23 @@ int sph_slab_p2p_density(sph_handle *h)
         in.flag[side] = (const uint32_t *)(h->mailbox + L.flag[side][P2P_RHO]);
         in.first[side] = (uint32_t)h->ghost_first[side];
     }
-    k_p2p_rho_pack<<<dim3(blocks_for(cap, SLAB_THREADS), 2), SLAB_THREADS, 0, s>>>(
+    // With the overlap on, the exchange runs on the second stream while the main stream integrates the rows
+    // that have no ghost among their neighbours (sph_slab_step_forces); the boundary rows' launch waits for it.
+    cudaStream_t xs = s;
+    if (h->p2p_overlap) {
+        CK(cudaEventRecord(h->ev_dens, s));
+        CK(cudaStreamWaitEvent(h->stream2, h->ev_dens, 0));
+        xs = h->stream2;
+    }
+    k_p2p_rho_pack<<<dim3(blocks_for(cap, SLAB_THREADS), 2), SLAB_THREADS, 0, xs>>>(
         h->vel[h->cur], h->inverse, h->halo_rows[0], h->halo_rows[1], cur, cap, out[0], out[1], p2p_publish_desc(h, P2P_RHO));
     CK_STEP_LAUNCH();
-    k_p2p_rho_apply<<<dim3(std::min(blocks_for(cap, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2), 2), SLAB_THREADS, 0, s>>>(in, cap, h->p2p_epoch, h->vel[h->cur],
+    k_p2p_rho_apply<<<dim3(std::min(blocks_for(cap, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2), 2), SLAB_THREADS, 0, xs>>>(in, cap, h->p2p_epoch, h->vel[h->cur],
                                                                                    h->inverse, &h->ctr->aux[3], cur);
+    if (h->p2p_overlap) {
+        CK(cudaEventRecord(h->ev_rho, xs));
+        h->rho_pending = true;
+    }
     CK_STEP_LAUNCH();
     return SPH_OK;
 }

@@ -52,6 +52,7 @@ struct StepCounters {
     uint32_t heavy[2];    // particles deferred to the warp-cooperative density / force kernels
     uint32_t epoch;       // tag of the current scan's tile states; bumped on the device so a captured step replays
     uint32_t fast_x;      // some particle moved half a cell or more along x in the last integration (slab edge scans)
+    uint32_t interior[2]; // slab mode: sorted rows [interior[0], interior[1]) have no ghost among their neighbours
 };
 
 // Settings + derived constants, passed to kernels by value.

@@ -350,12 +350,29 @@ __global__ void k_scan_arm(uint32_t *ticket, uint32_t *epoch)
 __global__ void __launch_bounds__(GRID_THREADS)
 k_place(const uint2 *__restrict__ cell_rank, const float4 *__restrict__ pos, uint32_t n,
         const uint32_t *__restrict__ starts, uint2 *__restrict__ slot, const GridDesc *__restrict__ gd,
-        StepCounters *publish_rows)
+        StepCounters *publish_rows, int slab_lo, int slab_hi)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // slab mode: the rows that survive the build (= the scan's end sentinel) are published for the gather
-    // kernel and for the host (this used to be a one-thread kernel of its own)
-    if (publish_rows && i == 0) publish_rows->aux[2] = starts[gd->ncells];
+    // kernel and for the host (this used to be a one-thread kernel of its own), and so is the range of
+    // sorted rows that cannot have a ghost among their neighbours: the owned rows of the x-layers
+    // slab_lo + 1 .. slab_hi - 2 (x is the slowest index: one contiguous range). The force pass of those
+    // rows does not have to wait for the ghosts' densities. Empty when something was clamped into the grid
+    // (ghost and owned rows may then share a layer).
+    if (publish_rows && i == 0) {
+        const GridDesc g = *gd;
+        const uint32_t rows = starts[g.ncells];
+        publish_rows->aux[2] = rows;
+        uint32_t r0 = 0, r1 = 0;
+        if (publish_rows->clamped == 0u && (long long)slab_hi - (long long)slab_lo > 2) {
+            const long long a = min(max((long long)slab_lo + 1 - g.ox, 0LL), (long long)g.nx);
+            const long long b = min(max((long long)slab_hi - 1 - g.ox, 0LL), (long long)g.nx);
+            r0 = starts[(uint32_t)a * g.sx];
+            r1 = b > a ? starts[(uint32_t)b * g.sx] : r0;
+        }
+        publish_rows->interior[0] = r0;
+        publish_rows->interior[1] = r1;
+    }
     if (i >= n) return;
     const uint2 cr = cell_rank[i];
     if (cr.x == CELL_NONE) return;

@@ -227,9 +227,10 @@ np.savez(sys.argv[1], steps=st.steps, launches=sim.launch_count, **{f"{n}_{k}": 
             assert_bit_equal(outs[0][k], outs[1][k], f"graph replay vs host launches: {k}")
 
 
-def test_tile_staged_force_kernel_returns_the_same_bits():
-    """SPH_B200_FORCES_CFG=6 stages each block's neighbourhoods in shared memory (kept as a measured
-    alternative). Same lists, same order, so the same bits as the default kernel."""
+def test_force_kernel_variants_return_the_same_bits():
+    """SPH_B200_FORCES_CFG: default = force terms with x, y packed as fp32x2; 7 = the scalar form; 6 stages
+    each block's neighbourhoods in shared memory (kept as a measured alternative). Same lists,
+    same order, the same rounded operations: the same bits."""
     code = r'''
 import sys, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r)
@@ -242,7 +243,7 @@ np.savez(sys.argv[1], **sim.download(S.ORDER_ID))
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         outs = []
-        for cfg in ("0", "6"):
+        for cfg in ("2", "6", "7"):
             env = dict(os.environ)
             env["SPH_B200_FORCES_CFG"] = cfg
             f = os.path.join(d, f"f{cfg}.npz")
@@ -250,6 +251,7 @@ np.savez(sys.argv[1], **sim.download(S.ORDER_ID))
             outs.append(dict(np.load(f)))
     for k in ("pos", "vel", "force", "density"):
         assert_bit_equal(outs[1][k], outs[0][k], f"tile-staged forces: {k}")
+        assert_bit_equal(outs[2][k], outs[0][k], f"scalar force terms: {k}")
 
 
 def test_device_scene_generators_and_reset_point(sph):
