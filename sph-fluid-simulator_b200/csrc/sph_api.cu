@@ -73,7 +73,7 @@ struct sph_handle {
     int slab_lo = 0, slab_hi = 0;  // this rank's x-cell range in the current sync-free step (0, 0: unknown -> no interior range)
     cudaStream_t stream2 = nullptr;  // peer steps: the density exchange runs here, next to the interior rows' force pass
     cudaEvent_t ev_dens = nullptr, ev_rho = nullptr;
-    bool p2p_overlap = true;       // SPH_B200_P2P_OVERLAP=0: everything on one stream, one force launch
+    bool p2p_overlap = false;      // SPH_B200_P2P_OVERLAP=1: density exchange on the second stream, force pass split (measured: no gain)
     bool rho_pending = false;      // ev_rho has been recorded for this step's force pass to wait on
     bool p2p_clean = false;   // the peer step's device cursors / done-counters are zero (it re-zeroes them itself)
     int forces_cfg = 0, density_cfg = 0;
@@ -693,7 +693,13 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaHostAlloc(&nh->pinned_rows, 2 * sizeof(uint32_t), cudaHostAllocDefault));
     nh->pinned_rows[0] = nh->pinned_rows[1] = 0;
     CKC(cudaEventCreateWithFlags(&nh->ev_rows, cudaEventDisableTiming));
-    CKC(cudaStreamCreateWithFlags(&nh->stream2, cudaStreamNonBlocking));
+    {
+        // highest priority: its few small exchange kernels must get SM slots while the main stream's force pass has
+        // tens of thousands of blocks queued (at equal priority they only start when that grid has been issued)
+        int prio_lo = 0, prio_hi = 0;
+        CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CKC(cudaStreamCreateWithPriority(&nh->stream2, cudaStreamNonBlocking, prio_hi));
+    }
     CKC(cudaEventCreateWithFlags(&nh->ev_dens, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&nh->ev_rho, cudaEventDisableTiming));
     if (const char *e = std::getenv("SPH_B200_P2P_OVERLAP")) nh->p2p_overlap = std::atoi(e) != 0;

@@ -145,6 +145,25 @@ def test_edge_scans_are_bit_identical_and_fall_back_for_fast_particles(sph, edge
     _compare(ranks, want, world)
 
 
+def test_overlapped_density_exchange_is_bit_identical(sph):
+    """SPH_B200_P2P_OVERLAP=1: the halo densities travel on a second stream while the rows without ghost
+    neighbours are integrated, the boundary rows follow in a second launch (opt-in: measured, no gain)."""
+    old = os.environ.get("SPH_B200_P2P_OVERLAP")
+    os.environ["SPH_B200_P2P_OVERLAP"] = "1"
+    try:
+        steps, world = 6, 3
+        with tempfile.TemporaryDirectory() as d:
+            want = _single_gpu_reference(sph, steps, d)
+            mp.spawn(_worker, args=(world, _free_port(), "gloo", steps, "p2p", d), nprocs=world, join=True)
+            ranks = [dict(np.load(os.path.join(d, f"rank{r}.npz"))) for r in range(world)]
+        _compare(ranks, want, world)
+    finally:
+        if old is None:
+            del os.environ["SPH_B200_P2P_OVERLAP"]
+        else:
+            os.environ["SPH_B200_P2P_OVERLAP"] = old
+
+
 @pytest.mark.parametrize("fast", [False, True, "p2p"], ids=["general", "syncfree", "peer-mailbox"])
 def test_slab_step_over_nccl(sph, fast):
     if torch.cuda.device_count() < 2:
