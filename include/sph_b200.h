@@ -325,20 +325,22 @@ int sph_slab_fast_set_ghost_density(sph_handle *h, const void *dev_recv_left, co
 
 
 /* Peer-memory variant of the sync-free step (one box, NVLink/NVSwitch): instead of packing into a
- * send buffer and handing it to NCCL, the pack kernels store rows straight into the adjacent
- * rank's mailbox (a device allocation exported with CUDA IPC), a one-thread kernel publishes the
- * row count and raises an epoch flag in the peer's memory, and the receiving stream spins on its
- * own flag before appending. No collective library is involved in the step at all.
+ * send buffer and handing it to NCCL, ONE pack kernel stores migrants and halo rows straight into the
+ * adjacent ranks' mailboxes (device allocations exported with CUDA IPC); its last block publishes the row
+ * counts and raises an epoch flag in the peers' memory, and the receiving kernel (one launch appends both
+ * neighbours' arrivals and ghosts) spins on its own flag first. A migrant that lands in the neighbour's
+ * boundary layer stays with the sender as a ghost (the neighbour would send it straight back), so the halo
+ * messages do not wait for the migrants: one exchange round for rows, one for densities. No collective
+ * library is involved in the step at all. Slabs must be at least three x-cells wide.
  * Setup: every rank calls sph_slab_p2p_create (64-byte IPC handle out), the handles are exchanged by
  * the caller, then sph_slab_p2p_connect(side 0 = left neighbour, 1 = right) for each neighbour.
- * Step: p2p_begin -> p2p_arrivals -> p2p_halo -> p2p_ghosts -> sph_slab_step_density ->
- * p2p_density -> sph_slab_step_forces; all ranks must step in lockstep. */
+ * Step: p2p_begin -> p2p_arrivals -> sph_slab_step_density -> p2p_density -> sph_slab_step_forces; all
+ * ranks must step in lockstep. migrant_rows = capacity of this step's migrant messages (0 or more than
+ * the mailbox holds: the mailbox's): a few thousand in steady state, a whole layer right after cuts moved. */
 int sph_slab_p2p_create(sph_handle *h, uint64_t halo_rows, uint64_t migrant_rows, void *ipc_handle_out64);
 int sph_slab_p2p_connect(sph_handle *h, int side, const void *peer_ipc_handle64);
-int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next);
+int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next, uint64_t migrant_rows);
 int sph_slab_p2p_arrivals(sph_handle *h);
-int sph_slab_p2p_halo(sph_handle *h, int32_t lo, int32_t hi);
-int sph_slab_p2p_ghosts(sph_handle *h);
 int sph_slab_p2p_density(sph_handle *h);
 
 #ifdef __cplusplus

@@ -129,10 +129,8 @@ def load_library() -> C.CDLL:
         "sph_slab_fast_set_ghost_density": ([hp, C.c_void_p, C.c_void_p, C.c_uint64], C.c_int),
         "sph_slab_p2p_create": ([hp, C.c_uint64, C.c_uint64, C.c_void_p], C.c_int),
         "sph_slab_p2p_connect": ([hp, C.c_int, C.c_void_p], C.c_int),
-        "sph_slab_p2p_begin": ([hp, C.c_int32, C.c_int32, C.c_int32, C.c_int32], C.c_int),
+        "sph_slab_p2p_begin": ([hp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64], C.c_int),
         "sph_slab_p2p_arrivals": ([hp], C.c_int),
-        "sph_slab_p2p_halo": ([hp, C.c_int32, C.c_int32], C.c_int),
-        "sph_slab_p2p_ghosts": ([hp], C.c_int),
         "sph_slab_p2p_density": ([hp], C.c_int),
         "sph_system_create": ([C.c_int, sp, C.c_int, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
         "sph_system_destroy": ([hp], C.c_int),

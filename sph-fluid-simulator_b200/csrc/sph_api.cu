@@ -70,6 +70,10 @@ struct sph_handle {
     P2PLayout p2p{};
     uint64_t p2p_H = 0, p2p_M = 0;
     uint32_t p2p_epoch = 0;
+    uint64_t p2p_M_step = 0;            // migrant message capacity of the current step (<= p2p_M)
+    uint32_t *mig_rows[2] = {nullptr, nullptr};  // per migrant slot: the local row kept as a ghost, or P2P_NO_ROW
+    uint64_t arr_first[2] = {0, 0};    // pre-sort row of the first arrival of each side
+    int p2p_lo = 0, p2p_hi = 0;    // this rank's cuts in the current peer step
     int slab_lo = 0, slab_hi = 0;  // this rank's x-cell range in the current sync-free step (0, 0: unknown -> no interior range)
     cudaStream_t stream2 = nullptr;  // peer steps: the density exchange runs here, next to the interior rows' force pass
     cudaEvent_t ev_dens = nullptr, ev_rho = nullptr;
@@ -724,7 +728,7 @@ int sph_destroy(sph_handle *h)
     cudaFree(h->stats_acc); cudaFree(h->scratch); cudaFree(h->reset_pos); cudaFree(h->reset_vel);
     for (int k = 0; k < 2; ++k)
         if (h->peer_mailbox[k]) cudaIpcCloseMemHandle(h->peer_mailbox[k]);
-    cudaFree(h->mailbox);
+    cudaFree(h->mailbox); cudaFree(h->mig_rows[0]); cudaFree(h->mig_rows[1]);
     drop_graphs(h);
     if (h->pinned_rows) cudaFreeHost(h->pinned_rows);
     if (h->ev_rows) cudaEventDestroy(h->ev_rows);
@@ -1728,7 +1732,7 @@ int sph_slab_fast_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, 
         k_slab_fast_begin<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dev_send_left ? lo : -0x7fffffff - 1,
             dev_send_right ? hi : 0x7fffffff, lo_prev, hi_next, (uint32_t)cap_rows, (float4 *)dev_send_left,
-            (float4 *)dev_send_right, cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all, P2PPublish{});
+            (float4 *)dev_send_right, cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all);
         CK_LAUNCH();
     }
     h->slab_fast = true;
@@ -1779,7 +1783,7 @@ int sph_slab_fast_halo(sph_handle *h, int32_t lo, int32_t hi, uint64_t cap_rows,
             h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dev_send_left != nullptr,
             dev_send_right != nullptr, (uint32_t)cap_rows, (float4 *)dev_send_left, (float4 *)dev_send_right,
             h->halo_rows[0], h->halo_rows[1], h->slab_counts + 2 * SLAB_MAX_RANKS, &h->ctr->aux[3], h->gd, h->cells,
-            h->ctr, (uint32_t)h->edge_sorted, h->edge_all, P2PPublish{});
+            h->ctr, (uint32_t)h->edge_sorted, h->edge_all);
         CK_LAUNCH();
     }
     h->fast_halo_cap = cap_rows;
@@ -1844,13 +1848,13 @@ int sph_slab_p2p_create(sph_handle *h, uint64_t halo_rows, uint64_t migrant_rows
         for (int b = 0; b < 2; ++b) {
             L.mig[s2][b] = take(migrant_rows * 32);
             L.halo[s2][b] = take(halo_rows * 32);
-            L.rho[s2][b] = take(halo_rows * 4);
+            L.rho[s2][b] = take((halo_rows + migrant_rows) * 4);  // halo densities, then those of the arrivals
         }
-    for (int s2 = 0; s2 < 2; ++s2)
-        for (int t = 0; t < 3; ++t) {
+    for (int s2 = 0; s2 < 2; ++s2) {
+        for (int t = 0; t < 3; ++t)
             for (int b = 0; b < 2; ++b) L.count[s2][t][b] = take(4);
-            L.flag[s2][t] = take(4);
-        }
+        for (int f = 0; f < 2; ++f) L.flag[s2][f] = take(4);
+    }
     L.bytes = off;
     CK(cudaMalloc(&h->mailbox, L.bytes));
     CK(cudaMemset(h->mailbox, 0, L.bytes));
@@ -1861,6 +1865,10 @@ int sph_slab_p2p_create(sph_handle *h, uint64_t halo_rows, uint64_t migrant_rows
     h->p2p_H = halo_rows;
     h->p2p_M = migrant_rows;
     h->p2p_epoch = 0;
+    if (!h->mig_rows[0]) {
+        CK(cudaMalloc(&h->mig_rows[0], sizeof(uint32_t) * migrant_rows));
+        CK(cudaMalloc(&h->mig_rows[1], sizeof(uint32_t) * migrant_rows));
+    }
     return SPH_OK;
 }
 
@@ -1884,131 +1892,117 @@ namespace {
 inline char *peer_slot(sph_handle *h, int to_side, unsigned long long off) { return h->peer_mailbox[to_side] + off; }
 }  // namespace
 
-// What the last block of a pack kernel of message type `type` publishes to the two neighbours.
-static P2PPublish p2p_publish_desc(sph_handle *h, int type)
-{
-    const P2PLayout &L = h->p2p;
-    const int b = h->p2p_epoch & 1;
-    P2PPublish pub{};
-    for (int side = 0; side < 2; ++side)
-        if (h->peer_mailbox[side]) {
-            pub.peer_count[side] = (uint32_t *)peer_slot(h, side, L.count[side ^ 1][type][b]);
-            pub.peer_flag[side] = (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][type]);
-        }
-    pub.done = reinterpret_cast<unsigned int *>(h->slab_counts + 2 * SLAB_MAX_RANKS + P2P_CUR_WORDS) + type;
-    pub.epoch = h->p2p_epoch;
-    pub.cap = (uint32_t)(type == P2P_MIG ? h->p2p_M : h->p2p_H);
-    return pub;
-}
-
-int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next)
+int sph_slab_p2p_begin(sph_handle *h, int32_t lo, int32_t hi, int32_t lo_prev, int32_t hi_next, uint64_t migrant_rows)
 {
     int rc = enter_exact(h);
     if (rc) return rc;
     if (!h->have_state || !h->slab_mode || !h->mailbox) return fail(h, SPH_ERR_STATE, "slab mode with a mailbox required");
+    if (h->n == 0) return fail(h, SPH_ERR_STATE, "a peer step needs at least one row on every rank");
+    const bool has_l = h->peer_mailbox[0] != nullptr, has_r = h->peer_mailbox[1] != nullptr;
+    if ((has_l || has_r) && (long long)hi - (long long)lo < 3 && (has_l ? 1 : 0) + (has_r ? 1 : 0) + ((long long)hi - lo) < 4)
+        return fail(h, SPH_ERR_INVALID, "a slab of %lld x-cells is too narrow for the peer step (3 needed): use the NCCL transport",
+                    (long long)hi - (long long)lo);
+    if (migrant_rows == 0 || migrant_rows > h->p2p_M) migrant_rows = h->p2p_M;
     cudaStream_t s = h->stream;
     ++h->p2p_epoch;
     const int b = h->p2p_epoch & 1;
     const P2PLayout &L = h->p2p;
     unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
+    unsigned int *done = reinterpret_cast<unsigned int *>(cur + P2P_CUR_WORDS);
+    uint32_t *saved = done + P2P_DONE_WORDS;  // [type][side]
     if (!h->p2p_clean) {  // first peer step, or the general path used these words since: the step itself re-zeroes them
         CK(cudaMemsetAsync(cur, 0, (P2P_CUR_WORDS + P2P_DONE_WORDS / 2) * sizeof(unsigned long long), s));
         h->p2p_clean = true;
     }
     // The violation word (aux[3]) is NOT cleared here: a time-out raised by the density leg of the previous
     // step — after that step's copy to the host — is picked up by this step's copy and reported by the next.
-    float4 *dst[2] = {nullptr, nullptr};
-    for (int side = 0; side < 2; ++side)
-        if (h->peer_mailbox[side]) dst[side] = (float4 *)peer_slot(h, side, L.mig[side ^ 1][b]);
-    begin_edge_scans(h);
-    if (h->n) {
-        // migrants stored straight into the neighbours' mailboxes; the last block publishes counts and flags
-        k_slab_fast_begin<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
-            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, dst[0] ? lo : -0x7fffffff - 1, dst[1] ? hi : 0x7fffffff,
-            lo_prev, hi_next, (uint32_t)h->p2p_M, dst[0], dst[1], cur, &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all,
-            p2p_publish_desc(h, P2P_MIG));
-        CK_STEP_LAUNCH();
-    } else {
-        return fail(h, SPH_ERR_STATE, "a peer step needs at least one row on every rank");
+    P2PPublish pub{};
+    float4 *mig[2] = {nullptr, nullptr}, *halo[2] = {nullptr, nullptr};
+    for (int side = 0; side < 2; ++side) {
+        if (!h->peer_mailbox[side]) continue;
+        mig[side] = (float4 *)peer_slot(h, side, L.mig[side ^ 1][b]);
+        halo[side] = (float4 *)peer_slot(h, side, L.halo[side ^ 1][b]);
+        pub.peer_count[0][side] = (uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_MIG][b]);
+        pub.peer_count[1][side] = (uint32_t *)peer_slot(h, side, L.count[side ^ 1][P2P_HALO][b]);
+        pub.peer_flag[side] = (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][0]);
+        pub.cursor[0][side] = cur + side;
+        pub.cursor[1][side] = cur + 2 + side;
+        pub.saved[0][side] = saved + side;
+        pub.saved[1][side] = saved + 2 + side;
     }
+    pub.cap[0] = (uint32_t)migrant_rows;
+    pub.cap[1] = (uint32_t)h->p2p_H;
+    pub.done = done;
+    pub.epoch = h->p2p_epoch;
+    pub.ntypes = 2;
+    begin_edge_scans(h);
+    // migrants and halo rows stored straight into the neighbours' mailboxes by one pass over the edge rows; the
+    // last block publishes the four counts and raises the two flags
+    k_p2p_pack<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
+        h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, lo_prev, hi_next, has_l, has_r, (uint32_t)migrant_rows,
+        (uint32_t)h->p2p_H, mig[0], mig[1], halo[0], halo[1], h->mig_rows[0], h->mig_rows[1], h->halo_rows[0], h->halo_rows[1], cur,
+        &h->ctr->aux[3], h->gd, h->cells, h->ctr, h->edge_all, pub);
+    CK_STEP_LAUNCH();
+    h->p2p_M_step = migrant_rows;
+    h->fast_halo_cap = h->p2p_H;
     h->slab_fast = true;
     h->n_ghost = 0;
     h->ghost_n[0] = h->ghost_n[1] = 0;
     h->have_step = false;
     // the x-layers of this slab that touch a neighbour's ghosts: lo (if there is a left neighbour), hi - 1 (right)
-    h->slab_lo = dst[0] ? lo : -0x3fffffff;
-    h->slab_hi = dst[1] ? hi : 0x3fffffff;
+    h->slab_lo = has_l ? lo : -0x3fffffff;
+    h->slab_hi = has_r ? hi : 0x3fffffff;
+    h->p2p_lo = lo;
+    h->p2p_hi = hi;
     return SPH_OK;
 }
 
-// Both incoming messages of one type appended behind the current rows by one kernel that waits for the flags.
-static int p2p_append(sph_handle *h, int type, bool ghost)
-{
-    const P2PLayout &L = h->p2p;
-    const int b = h->p2p_epoch & 1;
-    const uint64_t cap = type == P2P_MIG ? h->p2p_M : h->p2p_H;
-    const unsigned long long (*buf)[2] = type == P2P_MIG ? L.mig : L.halo;
-    P2PIncoming in{};
-    int nsides = 0;
-    for (int side = 0; side < 2; ++side) {
-        if (ghost) { h->ghost_first[side] = h->n; h->ghost_n[side] = h->peer_mailbox[side] ? cap : 0; }
-        if (!h->peer_mailbox[side]) continue;
-        if (h->n + cap > h->cap)
-            return fail(h, SPH_ERR_CAPACITY, "appending a %llu-row message to %llu rows exceeds capacity %llu",
-                        (unsigned long long)cap, (unsigned long long)h->n, (unsigned long long)h->cap);
-        in.rows[side] = (const float4 *)(h->mailbox + buf[side][b]);
-        in.count[side] = (const uint32_t *)(h->mailbox + L.count[side][type][b]);
-        in.flag[side] = (const uint32_t *)(h->mailbox + L.flag[side][type]);
-        in.first[side] = (uint32_t)h->n;
-        h->n += cap;
-        ++nsides;
-    }
-    if (nsides) {
-        // few blocks (they all poll the flag word first, see p2p_wait_flag): one per SM over the two sides
-        k_p2p_append<<<dim3(std::min(blocks_for(cap, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2), 2), SLAB_THREADS, 0, h->stream>>>(
-            in, (uint32_t)cap, h->p2p_epoch, ghost, h->pos[h->cur], h->vel[h->cur], &h->ctr->aux[3]);
-        CK_STEP_LAUNCH();
-    }
-    return SPH_OK;
-}
-
+// Both neighbours' migrant and halo messages appended behind the current rows by one kernel that waits for
+// their flags: regions [arrivals L][arrivals R][ghosts L][ghosts R] of fixed size.
 int sph_slab_p2p_arrivals(sph_handle *h)
 {
     int rc = enter(h);
     if (rc) return rc;
-    return p2p_append(h, P2P_MIG, false);
-}
-
-int sph_slab_p2p_halo(sph_handle *h, int32_t lo, int32_t hi)
-{
-    int rc = enter(h);
-    if (rc) return rc;
-    cudaStream_t s = h->stream;
     const P2PLayout &L = h->p2p;
     const int b = h->p2p_epoch & 1;
-    unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
-    float4 *dst[2] = {nullptr, nullptr};
-    for (int side = 0; side < 2; ++side)
-        if (h->peer_mailbox[side]) dst[side] = (float4 *)peer_slot(h, side, L.halo[side ^ 1][b]);
-    if (h->n) {
-        k_slab_fast_halo<<<edge_blocks(h), SLAB_THREADS, 0, s>>>(
-            h->pos[h->cur], h->vel[h->cur], (uint32_t)h->n, h->P.h, lo, hi, dst[0] != nullptr, dst[1] != nullptr,
-            (uint32_t)h->p2p_H, dst[0], dst[1], h->halo_rows[0], h->halo_rows[1], cur, &h->ctr->aux[3], h->gd, h->cells,
-            h->ctr, (uint32_t)h->edge_sorted, h->edge_all, p2p_publish_desc(h, P2P_HALO));
+    const uint64_t cm = h->p2p_M_step, ch = h->p2p_H;
+    P2PIncoming in{};
+    int nsides = 0;
+    for (int side = 0; side < 2; ++side) nsides += h->peer_mailbox[side] != nullptr;
+    if (h->n + (uint64_t)nsides * (cm + ch) > h->cap)
+        return fail(h, SPH_ERR_CAPACITY, "appending %d x (%llu + %llu) message rows to %llu rows exceeds capacity %llu", nsides,
+                    (unsigned long long)cm, (unsigned long long)ch, (unsigned long long)h->n, (unsigned long long)h->cap);
+    for (int side = 0; side < 2; ++side) {
+        h->arr_first[side] = h->n;
+        if (!h->peer_mailbox[side]) continue;
+        in.mig[side] = (const float4 *)(h->mailbox + L.mig[side][b]);
+        in.mig_count[side] = (const uint32_t *)(h->mailbox + L.count[side][P2P_MIG][b]);
+        in.flag[side] = (const uint32_t *)(h->mailbox + L.flag[side][0]);
+        in.mig_first[side] = (uint32_t)h->n;
+        h->n += cm;
+    }
+    for (int side = 0; side < 2; ++side) {
+        h->ghost_first[side] = h->n;
+        h->ghost_n[side] = h->peer_mailbox[side] ? ch : 0;
+        if (!h->peer_mailbox[side]) continue;
+        in.halo[side] = (const float4 *)(h->mailbox + L.halo[side][b]);
+        in.halo_count[side] = (const uint32_t *)(h->mailbox + L.count[side][P2P_HALO][b]);
+        in.halo_first[side] = (uint32_t)h->n;
+        h->n += ch;
+        h->n_ghost += ch;
+    }
+    if (nsides) {
+        // few blocks (they all poll the flag word first, see p2p_wait_flag): one per SM over the two sides
+        k_p2p_append<<<dim3(std::min(blocks_for(cm + ch, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2), 2), SLAB_THREADS, 0, h->stream>>>(
+            in, (uint32_t)cm, (uint32_t)ch, h->p2p_epoch, h->P.h, h->p2p_lo, h->p2p_hi, h->peer_mailbox[0] != nullptr,
+            h->peer_mailbox[1] != nullptr, h->pos[h->cur], h->vel[h->cur], &h->ctr->aux[3]);
         CK_STEP_LAUNCH();
     }
-    h->fast_halo_cap = h->p2p_H;
     return SPH_OK;
 }
 
-int sph_slab_p2p_ghosts(sph_handle *h)
-{
-    int rc = enter(h);
-    if (rc) return rc;
-    return p2p_append(h, P2P_HALO, true);
-}
-
-// Densities of my boundary rows into the neighbours' mailboxes, then the neighbours' into my ghosts.
+// Densities of my boundary rows and of this step's arrivals into the neighbours' mailboxes, then the
+// neighbours' into my ghosts (appended ones and the migrants I kept as ghosts).
 int sph_slab_p2p_density(sph_handle *h)
 {
     int rc = enter(h);
@@ -2016,20 +2010,32 @@ int sph_slab_p2p_density(sph_handle *h)
     cudaStream_t s = h->stream;
     const P2PLayout &L = h->p2p;
     const int b = h->p2p_epoch & 1;
-    const uint32_t cap = (uint32_t)h->p2p_H;
+    const uint32_t ch = (uint32_t)h->p2p_H, cm = (uint32_t)h->p2p_M_step;
     unsigned long long *cur = h->slab_counts + 2 * SLAB_MAX_RANKS;
+    unsigned int *done = reinterpret_cast<unsigned int *>(cur + P2P_CUR_WORDS);
+    uint32_t *saved = done + P2P_DONE_WORDS;
     if (!h->peer_mailbox[0] && !h->peer_mailbox[1]) return SPH_OK;
-    float *out[2] = {nullptr, nullptr};
-    P2PRhoIncoming in{};
+    P2PRhoOut o{};
+    P2PRhoIn in{};
+    P2PPublish pub{};
     for (int side = 0; side < 2; ++side) {
         if (!h->peer_mailbox[side]) continue;
-        out[side] = (float *)peer_slot(h, side, L.rho[side ^ 1][b]);
-        if (h->ghost_n[side] == 0) continue;
+        o.out[side] = (float *)peer_slot(h, side, L.rho[side ^ 1][b]);
+        o.halo_rows[side] = h->halo_rows[side];
+        o.halo_sent[side] = saved + 2 + side;
+        o.arrived[side] = (const uint32_t *)(h->mailbox + L.count[side][P2P_MIG][b]);
+        o.arr_first[side] = (uint32_t)h->arr_first[side];
+        pub.peer_flag[side] = (uint32_t *)peer_slot(h, side, L.flag[side ^ 1][1]);
         in.rho[side] = (const float *)(h->mailbox + L.rho[side][b]);
-        in.count[side] = (const uint32_t *)(h->mailbox + L.count[side][P2P_RHO][b]);
-        in.flag[side] = (const uint32_t *)(h->mailbox + L.flag[side][P2P_RHO]);
-        in.first[side] = (uint32_t)h->ghost_first[side];
+        in.flag[side] = (const uint32_t *)(h->mailbox + L.flag[side][1]);
+        in.halo_count[side] = (const uint32_t *)(h->mailbox + L.count[side][P2P_HALO][b]);
+        in.mig_sent[side] = saved + side;
+        in.mig_rows[side] = h->mig_rows[side];
+        in.ghost_first[side] = (uint32_t)h->ghost_first[side];
     }
+    pub.done = done + 1;
+    pub.epoch = h->p2p_epoch;
+    pub.ntypes = 0;
     // With the overlap on, the exchange runs on the second stream while the main stream integrates the rows
     // that have no ghost among their neighbours (sph_slab_step_forces); the boundary rows' launch waits for it.
     cudaStream_t xs = s;
@@ -2038,16 +2044,15 @@ int sph_slab_p2p_density(sph_handle *h)
         CK(cudaStreamWaitEvent(h->stream2, h->ev_dens, 0));
         xs = h->stream2;
     }
-    k_p2p_rho_pack<<<dim3(blocks_for(cap, SLAB_THREADS), 2), SLAB_THREADS, 0, xs>>>(
-        h->vel[h->cur], h->inverse, h->halo_rows[0], h->halo_rows[1], cur, cap, out[0], out[1], p2p_publish_desc(h, P2P_RHO));
+    const unsigned few = std::min(blocks_for(ch + cm, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2);
+    k_p2p_rho_pack<<<dim3(few, 2), SLAB_THREADS, 0, xs>>>(h->vel[h->cur], h->inverse, o, ch, cm, pub);
     CK_STEP_LAUNCH();
-    k_p2p_rho_apply<<<dim3(std::min(blocks_for(cap, SLAB_THREADS), (unsigned)(h->num_sms + 1) / 2), 2), SLAB_THREADS, 0, xs>>>(in, cap, h->p2p_epoch, h->vel[h->cur],
-                                                                                   h->inverse, &h->ctr->aux[3], cur);
+    k_p2p_rho_apply<<<dim3(few, 2), SLAB_THREADS, 0, xs>>>(in, ch, cm, h->p2p_epoch, h->vel[h->cur], h->inverse, &h->ctr->aux[3], cur);
+    CK_STEP_LAUNCH();
     if (h->p2p_overlap) {
         CK(cudaEventRecord(h->ev_rho, xs));
         h->rho_pending = true;
     }
-    CK_STEP_LAUNCH();
     return SPH_OK;
 }
 

@@ -109,33 +109,37 @@ constexpr uint32_t SLAB_ERR_MIGRANT_OVERFLOW = 1u, SLAB_ERR_HALO_OVERFLOW = 2u, 
 constexpr uint32_t SLAB_ERR_P2P_TIMEOUT = 8u;
 
 // Peer-memory transport (described at the end of this file): what the LAST block of a pack kernel
-// publishes to the adjacent ranks once every block has stored its rows — the row counts, then, after a
-// system-scope fence, the epoch flags the receivers spin on. done == nullptr: not a peer step.
+// publishes to the adjacent ranks once every block has stored its rows — the row counts of up to two
+// message types, then, after a system-scope fence, ONE epoch flag per neighbour that the receiver spins on.
 struct P2PPublish {
-    uint32_t *peer_count[2];  // [side] row count slot in the neighbour's mailbox (nullptr: no neighbour)
-    uint32_t *peer_flag[2];   // [side] epoch flag in the neighbour's mailbox
-    unsigned int *done;       // blocks of this kernel that have finished (zero at launch)
-    uint32_t epoch, cap;
+    uint32_t *peer_count[2][2];          // [type][side] count slot in the neighbour's mailbox (nullptr: none)
+    uint32_t *peer_flag[2];              // [side] epoch flag in the neighbour's mailbox (nullptr: no neighbour)
+    const unsigned long long *cursor[2][2];  // [type][side] local cursors the counts come from
+    uint32_t *saved[2][2];               // [type][side] local copy of the published count (read by later kernels)
+    uint32_t cap[2];                     // [type] message capacity
+    unsigned int *done;                  // blocks of this kernel that have finished (zero at launch)
+    uint32_t epoch;
+    int ntypes;
 };
 
 // Called by every thread at the end of a pack kernel (no thread may have returned early).
 // wrote: this thread stored rows into a peer mailbox.
-__device__ __forceinline__ void p2p_publish_when_last(const P2PPublish &pub, const unsigned long long *cursor_l,
-                                                      const unsigned long long *cursor_r, bool wrote)
+__device__ __forceinline__ void p2p_publish_when_last(const P2PPublish &pub, bool wrote)
 {
-    if (!pub.done) return;
     if (wrote) __threadfence_system();  // my rows are visible to the peer before anything ordered after this
     __syncthreads();
     if (threadIdx.x != 0) return;
     __threadfence();
     if (atomicAdd(pub.done, 1u) != gridDim.x * gridDim.y - 1u) return;
     __threadfence();  // every other block's cursor updates and fences are behind us
-    const unsigned long long *cur[2] = {cursor_l, cursor_r};
+    for (int t = 0; t < pub.ntypes; ++t)
 #pragma unroll
-    for (int side = 0; side < 2; ++side)
-        if (pub.peer_count[side]) {
-            const unsigned long long c = __ldcg(cur[side]);
-            *pub.peer_count[side] = (uint32_t)(c < pub.cap ? c : pub.cap);
+        for (int side = 0; side < 2; ++side) {
+            if (!pub.cursor[t][side]) continue;
+            const unsigned long long c = __ldcg(pub.cursor[t][side]);
+            const uint32_t cnt = (uint32_t)(c < pub.cap[t] ? c : pub.cap[t]);
+            if (pub.saved[t][side]) *pub.saved[t][side] = cnt;
+            if (pub.peer_count[t][side]) *pub.peer_count[t][side] = cnt;
         }
     __threadfence_system();
 #pragma unroll
@@ -212,15 +216,13 @@ __global__ void __launch_bounds__(SLAB_THREADS)
 k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int lo, int hi,
                   int lo_prev, int hi_next, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
                   unsigned long long *__restrict__ cur, uint32_t *__restrict__ err, const GridDesc *__restrict__ gd,
-                  const uint32_t *__restrict__ starts, const StepCounters *__restrict__ ctr, bool all,
-                  const P2PPublish pub)
+                  const uint32_t *__restrict__ starts, const StepCounters *__restrict__ ctr, bool all)
 {
     __shared__ EdgeScan s_e;
     if (threadIdx.x == 0) edge_scan_plan(s_e, *gd, starts, n, n, lo, hi, 1, all || ctr->fast_x != 0u);
     __syncthreads();
     const EdgeScan e = s_e;
     const uint32_t total = e.len[0] + e.len[1] + e.len[2];
-    bool wrote = false;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const uint32_t i = edge_scan_row(e, t);
         float4 p = pos[i];
@@ -244,7 +246,6 @@ k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint
                         dst[2 * k] = p;
                         dst[2 * k + 1] = v;
                         drop = true;
-                        wrote = true;
                     }
                 }
             }
@@ -254,7 +255,6 @@ k_slab_fast_begin(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint
             pos[i] = p;
         }
     }
-    p2p_publish_when_last(pub, &cur[0], &cur[1], wrote);
 }
 
 // Both halo messages in one pass over the edge rows (two layers deep: a row of layer lo + 1 may have
@@ -266,14 +266,13 @@ k_slab_fast_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
                  bool has_left, bool has_right, uint32_t cap, float4 *__restrict__ send_l, float4 *__restrict__ send_r,
                  uint32_t *__restrict__ rows_l, uint32_t *__restrict__ rows_r, unsigned long long *__restrict__ cur,
                  uint32_t *__restrict__ err, const GridDesc *__restrict__ gd, const uint32_t *__restrict__ starts,
-                 const StepCounters *__restrict__ ctr, uint32_t sorted, bool all, const P2PPublish pub)
+                 const StepCounters *__restrict__ ctr, uint32_t sorted, bool all)
 {
     __shared__ EdgeScan s_e;
     if (threadIdx.x == 0) edge_scan_plan(s_e, *gd, starts, n, sorted, lo, hi, 2, all || ctr->fast_x != 0u);
     __syncthreads();
     const EdgeScan e = s_e;
     const uint32_t total = e.len[0] + e.len[1] + e.len[2];
-    bool wrote = false;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
         const uint32_t i = edge_scan_row(e, t);
         const float4 p = pos[i];
@@ -286,16 +285,15 @@ k_slab_fast_halo(const float4 *__restrict__ pos, const float4 *__restrict__ vel,
         v.w = 0.f;
         if (to_l) {
             const unsigned long long k = atomicAdd(&cur[2], 1ull);
-            if (k < cap) { send_l[2 * k] = p; send_l[2 * k + 1] = v; rows_l[k] = i; wrote = true; }
+            if (k < cap) { send_l[2 * k] = p; send_l[2 * k + 1] = v; rows_l[k] = i; }
             else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
         }
         if (to_r) {
             const unsigned long long k = atomicAdd(&cur[3], 1ull);
-            if (k < cap) { send_r[2 * k] = p; send_r[2 * k + 1] = v; rows_r[k] = i; wrote = true; }
+            if (k < cap) { send_r[2 * k] = p; send_r[2 * k + 1] = v; rows_r[k] = i; }
             else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
         }
     }
-    p2p_publish_when_last(pub, &cur[2], &cur[3], wrote);
 }
 
 // Densities of the rows of one halo message; the message count is on the device (cursor). The
@@ -406,94 +404,205 @@ k_slab_xhist(const float4 *__restrict__ pos, uint32_t n, float h, int x_lo, uint
 // before it appends. Two buffers are enough: a sender reaches epoch e+2 only after it has waited
 // for the neighbour's epoch e+1 message, which the neighbour sent after consuming epoch e.
 struct P2PLayout {
-    unsigned long long mig[2][2], halo[2][2], rho[2][2];  // byte offsets [side][parity]
+    unsigned long long mig[2][2], halo[2][2], rho[2][2];  // byte offsets [side][parity]; rho = H + M floats
     unsigned long long count[2][3][2];                     // uint32 [side][type][parity]
-    unsigned long long flag[2][3];                         // uint32 [side][type]
+    unsigned long long flag[2][2];                         // uint32 [side][0 = rows (migrants + halo), 1 = densities]
     unsigned long long bytes;
 };
 enum { P2P_MIG = 0, P2P_HALO = 1, P2P_RHO = 2 };
+constexpr uint32_t P2P_NO_ROW = 0xFFFFFFFFu;
 
 // Device-side scratch of the peer step, in sph_handle::slab_counts behind the general path's counters:
-// cur[0..1] migrant cursors, cur[2..3] halo cursors, then one "blocks done" counter per publishing kernel.
-// All of it is zero when a peer step begins: k_p2p_rho_apply, the last exchange kernel of a step, re-zeroes it.
-constexpr int P2P_CUR_WORDS = 4;  // unsigned long long cursors
-constexpr int P2P_DONE_WORDS = 4; // unsigned int counters after them (migrants, halo, rho, spare)
+// cur[0..1] migrant cursors, cur[2..3] halo cursors, then two "blocks done" counters (rows kernel, density
+// kernel) and the four published counts saved for the density leg. All of it is zero when a peer step
+// begins: k_p2p_rho_apply, the last exchange kernel of a step, re-zeroes cursors and done-counters.
+constexpr int P2P_CUR_WORDS = 4;    // unsigned long long cursors
+constexpr int P2P_DONE_WORDS = 4;   // unsigned int: [0] rows kernel, [1] density kernel, [2..3] spare
+constexpr int P2P_SAVED_WORDS = 4;  // unsigned int after them: my published counts [type][side]
 
-// Both incoming messages of one type (side = blockIdx.y) appended behind the current rows, each into a
-// fixed region of `cap` rows: rows past the message's count become dropped rows. The block first waits for
-// the neighbour's flag (the flag-wait used to be a kernel of its own).
-struct P2PIncoming {
-    const float4 *rows[2];    // [side] message in the local mailbox (nullptr: no neighbour)
-    const uint32_t *count[2];
-    const uint32_t *flag[2];
-    uint32_t first[2];        // first destination row
-};
-
+// ONE pass over the slab's edge rows (two x-layers deep on either side; every row when a fast particle was
+// seen) that does what used to take two exchange rounds:
+//   * last step's ghosts are dropped;
+//   * an owned row whose cell.x left [lo, hi) is stored into the left / right neighbour's migrant message.
+//     If it lands in the neighbour's BOUNDARY layer (cell.x == lo - 1 or == hi) the neighbour would send it
+//     straight back as a ghost — so it simply stays here as a ghost (same position, same velocity), its slot
+//     remembered in mig_rows so that the density the new owner computes can find it; otherwise it is dropped;
+//   * an owned row that stays and lies in my first / last x-layer is stored into the left / right halo message.
+// An arrival never has to go into a halo message of the same step (the sender kept it, see above), so the
+// halo messages do not wait for the migrants any more: one kernel, one flag, one wait on the other side —
+// provided a slab is at least three cells wide (an arrival cannot reach the far boundary layer; checked on
+// arrival). The last block publishes all four counts and the flags.
 __global__ void __launch_bounds__(SLAB_THREADS)
-k_p2p_append(const P2PIncoming in, uint32_t cap, uint32_t epoch, bool ghost, float4 *__restrict__ pos,
-             float4 *__restrict__ vel, uint32_t *err)
+k_p2p_pack(float4 *__restrict__ pos, const float4 *__restrict__ vel, uint32_t n, float h, int lo, int hi, int lo_prev,
+           int hi_next, bool has_left, bool has_right, uint32_t cap_m, uint32_t cap_h, float4 *__restrict__ mig_l,
+           float4 *__restrict__ mig_r, float4 *__restrict__ halo_l, float4 *__restrict__ halo_r,
+           uint32_t *__restrict__ mig_rows_l, uint32_t *__restrict__ mig_rows_r, uint32_t *__restrict__ halo_rows_l,
+           uint32_t *__restrict__ halo_rows_r, unsigned long long *__restrict__ cur, uint32_t *__restrict__ err,
+           const GridDesc *__restrict__ gd, const uint32_t *__restrict__ starts, const StepCounters *__restrict__ ctr,
+           bool all, const P2PPublish pub)
 {
-    const int side = blockIdx.y;
-    if (!in.rows[side]) return;
-    p2p_wait_flag(in.flag[side], epoch, err);
-    const uint32_t first = in.first[side], count = *in.count[side];
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < cap; k += gridDim.x * blockDim.x) {
-        if (k >= count) {
-            pos[first + k] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
+    __shared__ EdgeScan s_e;
+    if (threadIdx.x == 0) edge_scan_plan(s_e, *gd, starts, n, n, lo, hi, 2, all || ctr->fast_x != 0u);
+    __syncthreads();
+    const EdgeScan e = s_e;
+    const uint32_t total = e.len[0] + e.len[1] + e.len[2];
+    bool wrote = false;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const uint32_t i = edge_scan_row(e, t);
+        float4 p = pos[i];
+        const uint32_t w = __float_as_uint(p.w);
+        if (w == W_DROP) continue;
+        if (w & W_GHOST) {  // last step's halo copy
+            p.w = __uint_as_float(W_DROP);
+            pos[i] = p;
             continue;
         }
-        float4 p = in.rows[side][2 * k];
-        const float4 v = in.rows[side][2 * k + 1];
-        uint32_t w = __float_as_uint(p.w) & W_ID_MASK;
-        if (ghost) w |= W_GHOST;
-        p.w = __uint_as_float(w);
-        pos[first + k] = p;
-        vel[first + k] = v;
-    }
-}
-
-// Densities of my boundary rows (the rows of the two halo messages, same order) stored into the
-// neighbours' mailboxes; the last block publishes counts and flags.
-__global__ void __launch_bounds__(SLAB_THREADS)
-k_p2p_rho_pack(const float4 *__restrict__ vel, const uint32_t *__restrict__ inverse, const uint32_t *__restrict__ rows_l,
-               const uint32_t *__restrict__ rows_r, const unsigned long long *__restrict__ cur, uint32_t cap,
-               float *__restrict__ out_l, float *__restrict__ out_r, const P2PPublish pub)
-{
-    const int side = blockIdx.y;
-    float *out = side ? out_r : out_l;
-    bool wrote = false;
-    if (out) {
-        const uint32_t *rows = side ? rows_r : rows_l;
-        const unsigned long long c = cur[2 + side];
-        const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-        if (k < cap && k < c) {
-            out[k] = vel[inverse[rows[k]]].w;
+        const int cx = cell_of(p.x, h);
+        const int side = (has_left && cx < lo) ? 0 : ((has_right && cx >= hi) ? 1 : -1);
+        if (side >= 0) {
+            if ((side == 0 && cx < lo_prev) || (side == 1 && cx >= hi_next)) {
+                atomicOr(err, SLAB_ERR_NOT_ADJACENT);
+                continue;
+            }
+            const unsigned long long k = atomicAdd(&cur[side], 1ull);
+            if (k >= cap_m) {
+                atomicOr(err, SLAB_ERR_MIGRANT_OVERFLOW);
+                continue;
+            }
+            float4 *dst = side == 0 ? mig_l : mig_r;
+            float4 v = vel[i];
+            v.w = 0.f;
+            dst[2 * k] = p;
+            dst[2 * k + 1] = v;
             wrote = true;
+            const bool keep = side == 0 ? cx == lo - 1 : cx == hi;
+            (side == 0 ? mig_rows_l : mig_rows_r)[k] = keep ? i : P2P_NO_ROW;
+            p.w = __uint_as_float(keep ? (w | W_GHOST) : W_DROP);
+            pos[i] = p;
+            continue;
+        }
+        const bool to_l = has_left && cx == lo, to_r = has_right && cx == hi - 1;
+        if (!to_l && !to_r) continue;
+        float4 v = vel[i];
+        v.w = 0.f;
+        if (to_l) {
+            const unsigned long long k = atomicAdd(&cur[2], 1ull);
+            if (k < cap_h) { halo_l[2 * k] = p; halo_l[2 * k + 1] = v; halo_rows_l[k] = i; wrote = true; }
+            else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
+        }
+        if (to_r) {
+            const unsigned long long k = atomicAdd(&cur[3], 1ull);
+            if (k < cap_h) { halo_r[2 * k] = p; halo_r[2 * k + 1] = v; halo_rows_r[k] = i; wrote = true; }
+            else atomicOr(err, SLAB_ERR_HALO_OVERFLOW);
         }
     }
-    p2p_publish_when_last(pub, &cur[2], &cur[3], wrote);
+    p2p_publish_when_last(pub, wrote);
 }
 
-// The neighbours' densities into my ghost rows (ghost batch `side` was appended at pre-sort rows
-// [first[side], first[side] + cap)); then the step's cursors and done-counters are zeroed for the next step.
-struct P2PRhoIncoming {
-    const float *rho[2];
-    const uint32_t *count[2];
+// Both neighbours' messages appended behind the current rows by one kernel (blockIdx.y = side): the arrivals
+// into a region of cap_m rows, the ghosts into a region of cap_h rows, rows past a message's count become
+// dropped rows. The block first waits for that neighbour's flag. An arrival that lands in my FAR boundary
+// layer would have had to be in a halo message that is already on its way: a violation (slab too narrow).
+struct P2PIncoming {
+    const float4 *mig[2], *halo[2];   // [side] messages in the local mailbox (nullptr: no neighbour)
+    const uint32_t *mig_count[2], *halo_count[2];
     const uint32_t *flag[2];
-    uint32_t first[2];
+    uint32_t mig_first[2], halo_first[2];  // first destination rows
 };
 
 __global__ void __launch_bounds__(SLAB_THREADS)
-k_p2p_rho_apply(const P2PRhoIncoming in, uint32_t cap, uint32_t epoch, float4 *__restrict__ vel,
+k_p2p_append(const P2PIncoming in, uint32_t cap_m, uint32_t cap_h, uint32_t epoch, float h, int lo, int hi, bool has_left,
+             bool has_right, float4 *__restrict__ pos, float4 *__restrict__ vel, uint32_t *err)
+{
+    const int side = blockIdx.y;
+    if (!in.mig[side]) return;
+    p2p_wait_flag(in.flag[side], epoch, err);
+    const uint32_t nm = *in.mig_count[side], nh = *in.halo_count[side];
+    const uint32_t total = cap_m + cap_h;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const bool ghost = t >= cap_m;
+        const uint32_t k = ghost ? t - cap_m : t;
+        const uint32_t row = (ghost ? in.halo_first[side] : in.mig_first[side]) + k;
+        if (k >= (ghost ? nh : nm)) {
+            pos[row] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
+            continue;
+        }
+        const float4 *src = ghost ? in.halo[side] : in.mig[side];
+        float4 p = src[2 * k];
+        const float4 v = src[2 * k + 1];
+        uint32_t w = __float_as_uint(p.w) & W_ID_MASK;
+        if (ghost) {
+            w |= W_GHOST;
+        } else {
+            const int cx = cell_of(p.x, h);
+            if ((side == 0 && has_right && cx >= hi - 1) || (side == 1 && has_left && cx <= lo)) atomicOr(err, SLAB_ERR_NOT_ADJACENT);
+        }
+        p.w = __uint_as_float(w);
+        pos[row] = p;
+        vel[row] = v;
+    }
+}
+
+// Densities into the neighbours' mailboxes (blockIdx.y = side): first those of the rows of my halo message to
+// that side (same order), then — at offset cap_h — those of the rows that ARRIVED from that side this step, in
+// the order of its migrant message (the sender kept some of them as ghosts and needs their densities back).
+struct P2PRhoOut {
+    float *out[2];                    // [side] density message in the neighbour's mailbox (nullptr: no neighbour)
+    const uint32_t *halo_rows[2];     // pre-sort rows of my halo messages
+    const uint32_t *halo_sent[2];     // saved counts of my halo messages
+    const uint32_t *arrived[2];       // counts of the migrant messages I received
+    uint32_t arr_first[2];            // pre-sort row of the first arrival of each side
+};
+
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_p2p_rho_pack(const float4 *__restrict__ vel, const uint32_t *__restrict__ inverse, const P2PRhoOut o, uint32_t cap_h,
+               uint32_t cap_m, const P2PPublish pub)
+{
+    const int side = blockIdx.y;
+    bool wrote = false;
+    if (o.out[side]) {
+        const uint32_t nh = *o.halo_sent[side], na = *o.arrived[side];
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < cap_h + cap_m; t += gridDim.x * blockDim.x) {
+            if (t < cap_h) {
+                if (t < nh) { o.out[side][t] = vel[inverse[o.halo_rows[side][t]]].w; wrote = true; }
+            } else if (t - cap_h < na) {
+                o.out[side][t] = vel[inverse[o.arr_first[side] + (t - cap_h)]].w;
+                wrote = true;
+            }
+        }
+    }
+    p2p_publish_when_last(pub, wrote);
+}
+
+// The neighbours' densities into my ghost rows (blockIdx.y = side): the appended ghost batch (pre-sort rows
+// ghost_first[side] + k) and the migrants I kept as ghosts (pre-sort row mig_rows[side][k] of slot k). Then the
+// step's cursors and done-counters are zeroed for the next step.
+struct P2PRhoIn {
+    const float *rho[2];
+    const uint32_t *flag[2];
+    const uint32_t *halo_count[2];    // count of the halo message I received from that side
+    const uint32_t *mig_sent[2];      // saved count of the migrant message I sent to that side
+    const uint32_t *mig_rows[2];
+    uint32_t ghost_first[2];
+};
+
+__global__ void __launch_bounds__(SLAB_THREADS)
+k_p2p_rho_apply(const P2PRhoIn in, uint32_t cap_h, uint32_t cap_m, uint32_t epoch, float4 *__restrict__ vel,
                 const uint32_t *__restrict__ inverse, uint32_t *err, unsigned long long *cur)
 {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < P2P_CUR_WORDS + P2P_DONE_WORDS / 2) cur[threadIdx.x] = 0ull;
     const int side = blockIdx.y;
     if (!in.rho[side]) return;
     p2p_wait_flag(in.flag[side], epoch, err);
-    const uint32_t count = min(cap, *in.count[side]);
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x)
-        vel[inverse[in.first[side] + k]].w = in.rho[side][k];
+    const uint32_t nh = min(cap_h, *in.halo_count[side]), nm = min(cap_m, *in.mig_sent[side]);
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < cap_h + cap_m; t += gridDim.x * blockDim.x) {
+        if (t < cap_h) {
+            if (t < nh) vel[inverse[in.ghost_first[side] + t]].w = in.rho[side][t];
+        } else if (t - cap_h < nm) {
+            const uint32_t r = in.mig_rows[side][t - cap_h];
+            if (r != P2P_NO_ROW) vel[inverse[r]].w = in.rho[side][t];
+        }
+    }
 }
 
 }  // namespace sphb

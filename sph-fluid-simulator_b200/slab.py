@@ -128,10 +128,10 @@ class GpuEngine:
         buf = (C.c_ubyte * 64)(*handle)
         self._ck(self.lib.sph_slab_p2p_connect(self.sim.handle, side, buf))
 
-    PHASES = ("migrate_out", "migrate_in", "halo_out", "halo_in", "grid+density", "halo_density", "forces")
+    PHASES = ("rows_out", "rows_in", "grid+density", "halo_density", "forces")
 
-    def p2p_step(self, lo, hi, lo_prev, hi_next, dt):
-        """One peer-mailbox step: 15 kernels, no host synchronisation. With self.phase_events set (a list),
+    def p2p_step(self, lo, hi, lo_prev, hi_next, dt, migrant_rows=0):
+        """One peer-mailbox step: 13 kernels, no host synchronisation. With self.phase_events set (a list),
         CUDA events are recorded on the library's stream between the phases (no synchronisation either)."""
         h, L = self.sim.handle, self.lib
         ev = None
@@ -139,20 +139,16 @@ class GpuEngine:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.PHASES) + 1)]
             self.phase_events.append(ev)
             ev[0].record(self.stream)
-        self._ck(L.sph_slab_p2p_begin(h, int(lo), int(hi), int(lo_prev), int(hi_next)))
+        self._ck(L.sph_slab_p2p_begin(h, int(lo), int(hi), int(lo_prev), int(hi_next), int(migrant_rows)))
         if ev: ev[1].record(self.stream)
         self._ck(L.sph_slab_p2p_arrivals(h))
         if ev: ev[2].record(self.stream)
-        self._ck(L.sph_slab_p2p_halo(h, int(lo), int(hi)))
-        if ev: ev[3].record(self.stream)
-        self._ck(L.sph_slab_p2p_ghosts(h))
-        if ev: ev[4].record(self.stream)
         self._ck(L.sph_slab_step_density(h))
-        if ev: ev[5].record(self.stream)
+        if ev: ev[3].record(self.stream)
         self._ck(L.sph_slab_p2p_density(h))
-        if ev: ev[6].record(self.stream)
+        if ev: ev[4].record(self.stream)
         self._ck(L.sph_slab_step_forces(h, C.c_float(dt)))
-        if ev: ev[7].record(self.stream)
+        if ev: ev[5].record(self.stream)
 
     def phase_ms(self):
         """Mean milliseconds per step of each phase over the steps recorded in self.phase_events (synchronises)."""
@@ -453,12 +449,12 @@ class SlabDriver:
         self.p2p_ready = True
         self.fast_H = int(halo_rows)
 
-    def step_p2p(self, dt: float = 0.0):
+    def step_p2p(self, dt: float = 0.0, migrant_rows: int = 0):
         """One step whose exchanges are stores into the neighbours' mailboxes: no collective calls,
-        no host synchronisation. All ranks must call it in lockstep; cuts must be unchanged since the
-        last general step()."""
+        no host synchronisation. All ranks must call it in lockstep; since the last step the cuts may have
+        moved by one cell each (pass migrant_rows = a whole layer then; 0 = the mailbox's capacity)."""
         r, w, c = self.rank, self.world, self.cuts
-        self.e.p2p_step(c[r], c[r + 1], c[r - 1] if r > 0 else INT_MIN, c[r + 2] if r < w - 1 else INT_MAX, dt)
+        self.e.p2p_step(c[r], c[r + 1], c[r - 1] if r > 0 else INT_MIN, c[r + 2] if r < w - 1 else INT_MAX, dt, migrant_rows)
         self.stats["steps"] += 1
 
     def _p2p(self, send, recv):
@@ -561,6 +557,7 @@ class SlabRunner:
         self.check_every, self.threshold, self.halo_slack = check_every, threshold, halo_slack
         self.k = 0
         self.general_steps = self.cut_moves = self.balance_checks = 0
+        self.layer_rows = 0
 
     def _first_step(self):
         d = self.d
@@ -569,6 +566,7 @@ class SlabRunner:
         self.general_steps += 1
         if d.world > 1 or self.transport != "general":
             rows = d.suggest_halo_rows(slack=self.halo_slack)
+            self.layer_rows = rows
             if self.transport == "p2p":
                 d.setup_p2p(rows, migrant_rows=rows)  # a whole layer may change hands when a cut moves
             elif self.transport == "nccl":
@@ -585,11 +583,15 @@ class SlabRunner:
                 d.step(self.dt)
                 self.general_steps += 1
             else:
+                moved = False
                 if self.k % self.check_every == 0 and d.world > 1:
                     self.balance_checks += 1
-                    self.cut_moves += bool(d.rebalance_incremental(self.threshold))
+                    moved = bool(d.rebalance_incremental(self.threshold))
+                    self.cut_moves += moved
                 if self.transport == "p2p":
-                    d.step_p2p(self.dt)
+                    # migrant messages: a whole layer right after a cut moved, an eighth of one otherwise (the
+                    # appended message regions are rows every kernel of the step has to look at)
+                    d.step_p2p(self.dt, 0 if moved else max(4096, self.layer_rows // 8))
                 else:
                     d.step_fast(self.dt)
             self.k += 1
