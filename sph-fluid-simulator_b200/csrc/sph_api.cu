@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "sph_device.cuh"
@@ -135,6 +136,7 @@ struct sph_handle {
     cudaGraphExec_t graphs[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [1 | kGraphLong steps][parity]
     uint64_t graph_launches[2] = {0, 0};  // kernel nodes of a captured 1-step / kGraphLong-step graph (counted at capture)
     bool graph_enabled = true;  // SPH_B200_GRAPH=0 launches every kernel from the host
+    bool pdl = false;           // SPH_B200_PDL=1: step kernels launched with programmatic dependent launch (measured: no gain)
 
     char err[512] = "";
 };
@@ -163,6 +165,29 @@ int fail(sph_handle *h, int code, const char *fmt, ...)
 #define CK_STEP_LAUNCH() do { CK(cudaGetLastError()); ++h->launches; } while (0)
 
 inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// Launch of a step kernel with programmatic stream serialization (pdl_enter in sph_device.cuh): the kernel's
+// blocks may become resident while the kernel in front of it drains and wait on the device for its completion,
+// which would hide launch latency between the nine kernels of a step. A captured step keeps these as
+// programmatic edges of the graph. Opt-in (SPH_B200_PDL=1): measured on B200 (tools/ab_env.py, bit-identical
+// either way) the captured step gains nothing — 0.2641 vs 0.2650 ms at 1 M, 0.9685 vs 0.9719 at 8 M — and the
+// 3 375-particle cube loses 2 us per step (29.2 vs 27.4): kernel nodes of a graph already follow each other
+// without a host-side gap, what is left between them is each kernel's own fill and drain.
+template <class... P, class... A>
+inline void launch_step(const sph_handle *h, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);  // a failure is picked up by CK_STEP_LAUNCH
+}
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -202,6 +227,11 @@ void make_params(const sph_settings &s, const sph_derived &d, Params &P)
     P.wall_offset = s.wall_offset;
     P.elasticity = s.elasticity;
     P.sphere_scale = d.sphere_scale;
+    P.clump_cell = CLUMP_CELL;
+    if (const char *e = std::getenv("SPH_B200_CLUMP_CELL")) {  // A/B and tests: 0 = every deferred row gets a warp
+        const long v = std::atol(e);
+        P.clump_cell = v <= 0 ? 0xFFFFFFFFu : (uint32_t)v;
+    }
 }
 
 int validate_settings(sph_handle *h, const sph_settings *s)
@@ -279,16 +309,16 @@ int build_grid(sph_handle *h)
     h->edge_ok = false;  // rows move; a slab force step declares them ordered again
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
-    k_plan_zero<<<h->num_sms * 8, GRID_THREADS, 0, s>>>(h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
+    launch_step(h, k_plan_zero, h->num_sms * 8, GRID_THREADS, 0, s, h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
     CK_STEP_LAUNCH();
-    k_cell_hist<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->pos[h->cur], n, h->P.h, h->gd, h->cells,
-                                                                   h->cell_rank, h->ctr);
+    launch_step(h, k_cell_hist, blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s, h->pos[h->cur], n, h->P.h, h->gd, h->cells,
+                h->cell_rank, h->ctr);
     CK_STEP_LAUNCH();
-    k_scan_exclusive<<<h->num_sms * 4, SCAN_THREADS, 0, s>>>(h->cells, &h->gd->ncells, h->tile_state,
-                                                            &h->ctr->ticket, &h->ctr->epoch);
+    launch_step(h, k_scan_exclusive, h->num_sms * 4, SCAN_THREADS, 0, s, h->cells, &h->gd->ncells, h->tile_state,
+                &h->ctr->ticket, &h->ctr->epoch);
     CK_STEP_LAUNCH();
-    k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->cells, h->slot, h->gd,
-                                                                   h->slab_mode ? h->ctr : nullptr, h->slab_lo, h->slab_hi);
+    launch_step(h, k_place, blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s, h->cell_rank, h->pos[h->cur], n, h->cells, h->slot,
+                h->gd, h->slab_mode ? h->ctr : nullptr, h->slab_lo, h->slab_hi);
     CK_STEP_LAUNCH();
     uint32_t n_sorted = n;
     const uint32_t *n_dev = nullptr;
@@ -306,9 +336,9 @@ int build_grid(sph_handle *h)
         }
     }
     if (n_sorted) {
-        k_order_gather<<<blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s>>>(
-            h->slot, h->cell_rank, n_sorted, n_dev, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1],
-            h->vel[h->cur ^ 1], h->hash16, h->slab_mode ? h->inverse : nullptr);
+        launch_step(h, k_order_gather, blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s,
+                    h->slot, h->cell_rank, n_sorted, n_dev, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1],
+                    h->vel[h->cur ^ 1], h->hash16, h->slab_mode ? h->inverse : nullptr);
         CK_STEP_LAUNCH();
     }
     h->cur ^= 1;
@@ -324,14 +354,18 @@ int launch_density(sph_handle *h, uint32_t n)
 {
     cudaStream_t s = h->stream;
 #define LAUNCH_D(S, B, U)                                                                                  \
-    k_density<S, B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                                  \
+    launch_step(h, k_density<S, B, U>, blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s,                       \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->ctr)
 #define LAUNCH_S(B, U)                                                                                     \
-    k_density_staged<B, U><<<blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s>>>(                              \
+    launch_step(h, k_density_staged<B, U>, blocks_for(n, PHYS_THREADS), PHYS_THREADS, 0, s,                   \
         h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap,      \
         h->order, h->ctr)
     int cfg = h->density_cfg;
+    // Default shape by size: once the rows no longer fit L2 (3 M rows x 32 B) the walk waits on memory and the
+    // 32-register shape's extra warps pay (0.398 vs 0.422 ms at 8 M rows); below, the 40-register one wins.
+    // Same bits either way.
+    if (cfg == 0 && n >= 3000000u) cfg = 3;
     if ((cfg < 10 || cfg >= 50) && (uint64_t)(NLIST_ROWS + 1) * h->cap >= (1ull << 32)) cfg = 10;
     if (cfg >= 50) {
         // TMA-staged neighbourhoods (measured alternative): persistent blocks, 3 per SM at 58 KB each
@@ -342,7 +376,7 @@ int launch_density(sph_handle *h, uint32_t n)
             h->tma_armed = true;
         }
         const unsigned tiles = blocks_for(n, PHYS_THREADS);
-        kern<<<std::min(tiles, (unsigned)h->num_sms * 3u), PHYS_THREADS, sizeof(TmaTile), s>>>(
+        launch_step(h, kern, std::min(tiles, (unsigned)h->num_sms * 3u), PHYS_THREADS, sizeof(TmaTile), s,
             h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur], h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
     } else
     switch (cfg) {
@@ -358,8 +392,8 @@ int launch_density(sph_handle *h, uint32_t n)
 #undef LAUNCH_S
     CK_STEP_LAUNCH();
     // the heavy tail (clumps, hash-collision cells), one warp per deferred particle; exits at once when empty
-    k_density_heavy<<<h->num_sms * 4, HEAVY_THREADS, 0, s>>>(h->pos[h->cur], h->gd, h->cells, h->P, h->vel[h->cur],
-                                                            h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
+    launch_step(h, k_density_heavy, h->num_sms * 4, HEAVY_THREADS, 0, s, h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
+                h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
     CK_STEP_LAUNCH();
     return SPH_OK;
 }
@@ -374,15 +408,17 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
     // FI_FORCE_ONLY reads the start-of-step rows, which after the step live in the non-current buffers
     const int in = mode == FI_FORCE_ONLY ? (h->cur ^ 1) : h->cur;
 #define LAUNCH_FI(T, B, M)                                                                                       \
-    k_forces_integrate<T, B, M><<<blocks_for(n, T), T, 0, s>>>(                                                   \
+    launch_step(h, k_forces_integrate<T, B, M>, blocks_for(n, T), T, 0, s,                                       \
         h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt,              \
         h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part)
 #define LAUNCH_FH(M)                                                                                              \
-    k_forces_heavy<M><<<h->num_sms * 4, HEAVY_THREADS, 0, s>>>(h->pos[in], h->vel[in], h->gd, h->cells, h->P, dt,  \
-                                                              h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr,   \
-                                                              h->parity ^ 1, h->map)
+    launch_step(h, k_forces_heavy<M>, h->num_sms * 4, HEAVY_THREADS, 0, s, h->pos[in], h->vel[in], n, h->gd, h->cells, \
+                h->P, h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map)
     if (mode == FI_FORCE_ONLY) {
         CK(cudaMemsetAsync(&h->ctr->heavy[1], 0, sizeof(uint32_t), s));  // the step's deferral list is rebuilt
+        CK(cudaMemsetAsync(&h->ctr->clump_tiles[1], 0, sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(&h->ctr->clump_rows[1], 0, sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(&h->ctr->clump_ticket[1], 0, sizeof(uint32_t), s));
         LAUNCH_FI(128, 10, FI_FORCE_ONLY);
     } else if (mode == FI_STEP_WRITE_FORCE) {
         LAUNCH_FI(128, 10, FI_STEP_WRITE_FORCE);
@@ -394,14 +430,14 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
             CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * CAPR));              \
             h->tile_armed = true;                                                                                \
         }                                                                                                        \
-        kern<<<blocks_for(n, T), T, 32 * CAPR, s>>>(h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist,   \
-                                                    h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1], h->vel[in ^ 1], \
-                                                    h->force, h->ctr, h->parity ^ 1, h->map);                     \
+        launch_step(h, kern, blocks_for(n, T), T, 32 * CAPR, s, h->pos[in], h->vel[in], n, h->gd, h->cells, h->P,  \
+                    h->nlist, h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr,    \
+                    h->parity ^ 1, h->map);                                                                      \
     } while (0)
         switch ((part != 0 && h->forces_cfg == 6) ? 2 : h->forces_cfg) {  // the tile-staged variant has no split form
         case 6: LAUNCH_FT(128, 5, 1408); break;  // shared-memory staged neighbourhoods: measured 2-4x slower
         case 7:  // the scalar form of the force terms (A/B against the packed default: same bits)
-            k_forces_integrate<128, 10, FI_STEP, false><<<blocks_for(n, 128), 128, 0, s>>>(
+            launch_step(h, k_forces_integrate<128, 10, FI_STEP, false>, blocks_for(n, 128), 128, 0, s,
                 h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1],
                 h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part);
             break;
@@ -663,6 +699,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_DENSITY_CFG")) nh->density_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_GRAPH")) nh->graph_enabled = std::atoi(e) != 0;
+    if (const char *e = std::getenv("SPH_B200_PDL")) nh->pdl = std::atoi(e) != 0;
     if (const char *e = std::getenv("SPH_B200_EDGE_SCAN")) nh->edge_scan_enabled = std::atoi(e) != 0;
     std::memset(&nh->graph_key, 0, sizeof nh->graph_key);
 
@@ -1292,8 +1329,8 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     out->grid_dim[0] = g.nx; out->grid_dim[1] = g.ny; out->grid_dim[2] = g.nz;
     out->grid_cells = g.ncells;
     out->clamped = c.clamped;
-    out->deferred_density = c.heavy[0];
-    out->deferred_forces = c.heavy[1];
+    out->deferred_density = c.heavy[0] + c.clump_rows[0];  // one warp per row + rows of the tiled clump kernels
+    out->deferred_forces = c.heavy[1] + c.clump_rows[1];
     out->nlist_rows = NLIST_ROWS;
     out->nan_count = a.nan_count;
     if (h->have_step) out->count = a.owned;

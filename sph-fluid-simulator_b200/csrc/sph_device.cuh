@@ -53,6 +53,9 @@ struct StepCounters {
     uint32_t epoch;       // tag of the current scan's tile states; bumped on the device so a captured step replays
     uint32_t fast_x;      // some particle moved half a cell or more along x in the last integration (slab edge scans)
     uint32_t interior[2]; // slab mode: sorted rows [interior[0], interior[1]) have no ghost among their neighbours
+    // clump rows (deferred rows of crowded cells, sph_physics.cuh): 32-row tiles registered by the density / force
+    // pass, the rows they stand for, and the ticket the tiled kernels draw tiles with
+    uint32_t clump_tiles[2], clump_rows[2], clump_ticket[2];
 };
 
 // Settings + derived constants, passed to kernels by value.
@@ -66,7 +69,21 @@ struct Params {
     float two_hmb;      // 2 * (settings.h - boxWidth)         (src/sph.cpp:159,169)
     float two_nhmb;     // 2 * -(settings.h - boxWidth)        (src/sph.cpp:164,174)
     float wall_offset, elasticity, sphere_scale;
+    uint32_t clump_cell;  // rows of a cell with at least this many rows are deferred as clump rows (sph_physics.cuh)
 };
+
+// ---- programmatic dependent launch -----------------------------------------------------------
+// The kernels of a step are launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_step
+// in sph_api.cu): the next kernel's blocks may become resident while this one drains, and they block here
+// until every block of the previous kernel has exited and its writes are visible. First statement of every
+// step kernel, executed by every thread before anything else: a block that left without waiting would let
+// its grid complete — and release the grid after it — before the grid in front of it has finished.
+// Without the launch attribute both instructions do nothing.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ---- cell and hash (bit-exact targets) ----------------------------------------------------
 

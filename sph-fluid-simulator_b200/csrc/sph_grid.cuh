@@ -190,6 +190,7 @@ __device__ __forceinline__ GridDesc plan_grid(const int *b, uint32_t max_cells, 
 __global__ void __launch_bounds__(GRID_THREADS)
 k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, int expand, uint32_t *__restrict__ counts)
 {
+    pdl_enter();
     __shared__ GridDesc s_g;
     if (threadIdx.x == 0) s_g = plan_grid(ctr->bbox[parity], max_cells, expand);
     __syncthreads();
@@ -206,6 +207,9 @@ k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, int
             ++ctr->epoch;
             ctr->clamped = 0;
             ctr->heavy[0] = ctr->heavy[1] = 0;
+            ctr->clump_tiles[0] = ctr->clump_tiles[1] = 0;
+            ctr->clump_rows[0] = ctr->clump_rows[1] = 0;
+            ctr->clump_ticket[0] = ctr->clump_ticket[1] = 0;
             ctr->fast_x = 0;  // consumed by this step's slab edge scans, set again by its integration
             int *nb = ctr->bbox[parity ^ 1];
             nb[0] = nb[1] = nb[2] = 0x7fffffff;
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(GRID_THREADS)
 k_cell_hist(const float4 *__restrict__ pos, uint32_t n, float h, const GridDesc *__restrict__ gd,
             uint32_t *__restrict__ counts, uint2 *__restrict__ cell_rank, StepCounters *ctr)
 {
+    pdl_enter();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const GridDesc g = *gd;
@@ -256,6 +261,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_exclusive(uint32_t *__restrict__ data, const uint32_t *__restrict__ n_ptr,
                  unsigned long long *tile_state, uint32_t *ticket, const uint32_t *__restrict__ epoch_ptr)
 {
+    pdl_enter();
     const uint32_t epoch = *epoch_ptr;
     __shared__ uint32_t s_tile, s_excl;
     __shared__ uint32_t s_wsum[SCAN_THREADS / 32];
@@ -352,6 +358,7 @@ k_place(const uint2 *__restrict__ cell_rank, const float4 *__restrict__ pos, uin
         const uint32_t *__restrict__ starts, uint2 *__restrict__ slot, const GridDesc *__restrict__ gd,
         StepCounters *publish_rows, int slab_lo, int slab_hi)
 {
+    pdl_enter();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // slab mode: the rows that survive the build (= the scan's end sentinel) are published for the gather
     // kernel and for the host (this used to be a one-thread kernel of its own), and so is the range of
@@ -408,6 +415,7 @@ k_order_gather(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_ra
                const float4 *__restrict__ pos_in, const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out,
                float4 *__restrict__ vel_out, uint32_t *__restrict__ hash_out, uint32_t *__restrict__ inverse)
 {
+    pdl_enter();
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_bound) return;
     // Sync-free slab mode: the host only knows an upper bound of the surviving rows; the exact

@@ -191,6 +191,75 @@ def test_clump_takes_the_warp_cooperative_kernels(sph, oracle):
         assert_bit_equal(runs[1][0][k], got[k], f"second run: {k}")
 
 
+def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
+    """nine runs (x offset outer, z offset inner), each the cells y-1, y, y+1 of a column in
+    ascending y, rows of a cell by ascending id; dens = (float)((double)dens + mp * t^3) per accepted row."""
+    f = np.float32
+    c = tuple(int(v) for v in np.trunc(pos[i] / f(h)).astype(np.int64))
+    dens, cnt, longest = f(0), 0, 0
+    for ox in (-1, 0, 1):
+        for oz in (-1, 0, 1):
+            run = 0
+            for oy in (-1, 0, 1):
+                for j in ids_by_cell.get((c[0] + ox, c[1] + oy, c[2] + oz), ()):
+                    run += 1
+                    if j == i:
+                        continue
+                    d = pos[j] - pos[i]
+                    d2 = f(f(f(d[0] * d[0]) + f(d[1] * d[1])) + f(d[2] * d[2]))
+                    if d2 < h2:
+                        t = np.float64(f(h2 - d2))
+                        dens = f(np.float64(dens) + np.float64(mp) * ((t * t) * t))
+                        cnt += 1
+            longest = max(longest, run)
+    return f(dens + self_dens), cnt, longest, len(ids_by_cell[c])
+
+
+def test_sums_are_taken_in_the_documented_order(sph):
+    """Bit-exact check of the summation order itself, against a numpy restatement: for rows of the one-thread
+    kernel and for clump rows (tiled phase of the heavy kernel), which promise the same sequence. Rows that get
+    a warp of their own (deferred, own cell below the clump threshold) sum by a fixed tree instead: skipped,
+    as are hash-collision neighbourhoods (multiplicities)."""
+    rng = np.random.default_rng(5)
+    s = sph.default_settings()
+    d = rng.normal(size=(1500, 3))
+    d *= (0.25 * rng.uniform(0, 1, (1500, 1)) ** (1 / 3)) / np.linalg.norm(d, axis=1, keepdims=True)
+    pos = np.concatenate([d + [1.0, 1.0, 1.0], rng.uniform([-3, 0.2, -3], [3, 3, 3], (2500, 3))]).astype(np.float32)
+    vel = np.zeros_like(pos)
+    sim = sph.Sim(s, capacity=len(pos))
+    sim.upload(pos, vel)
+    sim.step(1)
+    got = sim.download(sph.ORDER_ID, fields=("density",))["density"]
+    st = sim.stats()
+    sim.close()
+    assert st.deferred_density >= 1400
+    dv = sph.derive(s)
+    f = np.float32
+    h, h2, mp = f(s.h), f(dv.h2), f(f(s.mass) * f(dv.poly6))
+    cells = np.trunc(pos / h).astype(np.int64)
+    ids_by_cell = {}
+    for j, c in enumerate(map(tuple, cells)):
+        ids_by_cell.setdefault(c, []).append(j)
+    M = (73856093, 19349663, 83492791)
+
+    def collides(c):
+        hs = [((c[0] + x) * M[0] ^ (c[1] + y) * M[1] ^ (c[2] + z) * M[2]) & 0xFFFF
+              for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
+        return len(set(hs)) < 27
+
+    checked = {"light": 0, "clump": 0}
+    for i in list(rng.choice(1500, 60, replace=False)) + list(1500 + rng.choice(2500, 60, replace=False)):
+        if collides(tuple(cells[i])):
+            continue
+        want, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(dv.self_dens))
+        deferred = longest > 96 or cnt > st.nlist_rows
+        if deferred and own < 64:
+            continue  # one warp per row: tree sum
+        checked["clump" if deferred else "light"] += 1
+        assert got[i].view(np.uint32) == want.view(np.uint32), (i, deferred, cnt, float(got[i]), float(want))
+    assert checked["light"] >= 40 and checked["clump"] >= 10, checked
+
+
 def test_captured_steps_replay_the_same_bits():
     """sph_step replays CUDA graphs of 1 and 16 captured steps; SPH_B200_GRAPH=0 launches every kernel
     from the host. 37 = 2 x 16 + 5 steps, then a settings change (new key), an upload and 3 more."""
