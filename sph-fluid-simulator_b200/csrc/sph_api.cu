@@ -52,6 +52,7 @@ struct sph_handle {
     uint32_t *nlist = nullptr, *ncount = nullptr;  // neighbour lists written by the density pass
     uint2 *cell_rank = nullptr, *slot = nullptr;
     uint32_t *order = nullptr, *map = nullptr;
+    uint32_t *tile_claim = nullptr;  // per 32-row tile: the build epoch in which a warp claimed it; behind it, the claimed tiles
     uint32_t *inverse = nullptr;          // sorted row of each pre-sort row (slab mode)
     uint32_t *halo_rows[2] = {nullptr, nullptr};  // pre-sort rows packed into each halo message
     uint64_t halo_n[2] = {0, 0};
@@ -393,7 +394,7 @@ int launch_density(sph_handle *h, uint32_t n)
     CK_STEP_LAUNCH();
     // the heavy tail (clumps, hash-collision cells), one warp per deferred particle; exits at once when empty
     launch_step(h, k_density_heavy, h->num_sms * 4, HEAVY_THREADS, 0, s, h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
-                h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->ctr);
+                h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->tile_claim, h->tile_claim + h->cap / 32 + 1, h->ctr);
     CK_STEP_LAUNCH();
     return SPH_OK;
 }
@@ -413,12 +414,12 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
         h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part)
 #define LAUNCH_FH(M)                                                                                              \
     launch_step(h, k_forces_heavy<M>, h->num_sms * 4, HEAVY_THREADS, 0, s, h->pos[in], h->vel[in], n, h->gd, h->cells, \
-                h->P, h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map)
+                h->P, h->ncount, dt, h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map,             \
+                h->tile_claim + h->cap / 32 + 1)
     if (mode == FI_FORCE_ONLY) {
         CK(cudaMemsetAsync(&h->ctr->heavy[1], 0, sizeof(uint32_t), s));  // the step's deferral list is rebuilt
-        CK(cudaMemsetAsync(&h->ctr->clump_tiles[1], 0, sizeof(uint32_t), s));
         CK(cudaMemsetAsync(&h->ctr->clump_rows[1], 0, sizeof(uint32_t), s));
-        CK(cudaMemsetAsync(&h->ctr->clump_ticket[1], 0, sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(&h->ctr->clump_ticket[1], 0, 2 * sizeof(uint32_t), s));  // force list and tile tickets
         LAUNCH_FI(128, 10, FI_FORCE_ONLY);
     } else if (mode == FI_STEP_WRITE_FORCE) {
         LAUNCH_FI(128, 10, FI_STEP_WRITE_FORCE);
@@ -720,6 +721,8 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaMalloc(&nh->slab_counts, sizeof(unsigned long long) * (2 * SLAB_MAX_RANKS + 8)));
     CKC(cudaMalloc(&nh->order, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->map, sizeof(uint32_t) * cap));
+    CKC(cudaMalloc(&nh->tile_claim, sizeof(uint32_t) * 2 * (cap / 32 + 1)));
+    CKC(cudaMemsetAsync(nh->tile_claim, 0, sizeof(uint32_t) * 2 * (cap / 32 + 1), nh->stream));
     CKC(cudaMalloc(&nh->cells, sizeof(uint32_t) * ((size_t)nh->max_cells + 8)));
     CKC(cudaMalloc(&nh->h16_cells, sizeof(uint32_t) * 65540));
     CKC(cudaMalloc(&nh->const_65536, sizeof(uint32_t)));
@@ -760,7 +763,7 @@ int sph_destroy(sph_handle *h)
     for (int b = 0; b < 2; ++b) { cudaFree(h->pos[b]); cudaFree(h->vel[b]); }
     cudaFree(h->force); cudaFree(h->hash16); cudaFree(h->nlist); cudaFree(h->ncount); cudaFree(h->cell_rank); cudaFree(h->slot); cudaFree(h->inverse);
     cudaFree(h->halo_rows[0]); cudaFree(h->halo_rows[1]); cudaFree(h->slab_counts);
-    cudaFree(h->order); cudaFree(h->map); cudaFree(h->cells); cudaFree(h->h16_cells);
+    cudaFree(h->order); cudaFree(h->map); cudaFree(h->tile_claim); cudaFree(h->cells); cudaFree(h->h16_cells);
     cudaFree(h->const_65536); cudaFree(h->tile_state); cudaFree(h->gd); cudaFree(h->ctr);
     cudaFree(h->stats_acc); cudaFree(h->scratch); cudaFree(h->reset_pos); cudaFree(h->reset_vel);
     for (int k = 0; k < 2; ++k)
@@ -1329,8 +1332,8 @@ int sph_get_stats(sph_handle *h, sph_stats *out)
     out->grid_dim[0] = g.nx; out->grid_dim[1] = g.ny; out->grid_dim[2] = g.nz;
     out->grid_cells = g.ncells;
     out->clamped = c.clamped;
-    out->deferred_density = c.heavy[0] + c.clump_rows[0];  // one warp per row + rows of the tiled clump kernels
-    out->deferred_forces = c.heavy[1] + c.clump_rows[1];
+    out->deferred_density = c.heavy[0];                    // every deferred row, clump rows (served a tile at a time) included
+    out->deferred_forces = c.heavy[1] + c.clump_rows[1];   // rows the force pass deferred + the clump rows it served by tile
     out->nlist_rows = NLIST_ROWS;
     out->nan_count = a.nan_count;
     if (h->have_step) out->count = a.owned;

@@ -53,9 +53,10 @@ struct StepCounters {
     uint32_t epoch;       // tag of the current scan's tile states; bumped on the device so a captured step replays
     uint32_t fast_x;      // some particle moved half a cell or more along x in the last integration (slab edge scans)
     uint32_t interior[2]; // slab mode: sorted rows [interior[0], interior[1]) have no ghost among their neighbours
-    // clump rows (deferred rows of crowded cells, sph_physics.cuh): 32-row tiles registered by the density / force
-    // pass, the rows they stand for, and the ticket the tiled kernels draw tiles with
-    uint32_t clump_tiles[2], clump_rows[2], clump_ticket[2];
+    // clump rows (deferred rows of crowded cells, sph_physics.cuh): [0] 32-row tiles the density pass claimed (the
+    // force pass serves the same list), rows served by the tiled phase of each pass, and the tickets the heavy kernels
+    // draw work with: [0] density deferral list, [1] force deferral list, [2] tiles in the force pass
+    uint32_t clump_tiles[2], clump_rows[2], clump_ticket[3];
 };
 
 // Settings + derived constants, passed to kernels by value.

@@ -209,7 +209,7 @@ k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, int
             ctr->heavy[0] = ctr->heavy[1] = 0;
             ctr->clump_tiles[0] = ctr->clump_tiles[1] = 0;
             ctr->clump_rows[0] = ctr->clump_rows[1] = 0;
-            ctr->clump_ticket[0] = ctr->clump_ticket[1] = 0;
+            ctr->clump_ticket[0] = ctr->clump_ticket[1] = ctr->clump_ticket[2] = 0;
             ctr->fast_x = 0;  // consumed by this step's slab edge scans, set again by its integration
             int *nb = ctr->bbox[parity ^ 1];
             nb[0] = nb[1] = nb[2] = 0x7fffffff;
