@@ -52,7 +52,7 @@ struct sph_handle {
     uint32_t *nlist = nullptr, *ncount = nullptr;  // neighbour lists written by the density pass
     uint2 *cell_rank = nullptr, *slot = nullptr;
     uint32_t *order = nullptr, *map = nullptr;
-    uint32_t *tile_claim = nullptr;  // per 32-row tile: the build epoch in which a warp claimed it; behind it, the claimed tiles
+    uint32_t *tile_claim = nullptr;  // per tile of CLUMP_ROWS rows: the build epoch in which a warp claimed it; behind it, the claimed tiles
     uint32_t *inverse = nullptr;          // sorted row of each pre-sort row (slab mode)
     uint32_t *halo_rows[2] = {nullptr, nullptr};  // pre-sort rows packed into each halo message
     uint64_t halo_n[2] = {0, 0};
@@ -83,6 +83,7 @@ struct sph_handle {
     bool rho_pending = false;      // ev_rho has been recorded for this step's force pass to wait on
     bool p2p_clean = false;   // the peer step's device cursors / done-counters are zero (it re-zeroes them itself)
     int forces_cfg = 0, density_cfg = 0;
+    int heavy_blocks = HEAVY_BLOCKS_PER_SM;  // blocks per SM of the heavy kernels' persistent grids (SPH_B200_HEAVY_BLOCKS: A/B)
     // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
     // are in the cell order of the last build, i.e. from a slab force step until anything else touches them.
     bool edge_scan_enabled = true;   // SPH_B200_EDGE_SCAN=0 scans every row (see DESIGN.md §5 for the measurements)
@@ -393,8 +394,8 @@ int launch_density(sph_handle *h, uint32_t n)
 #undef LAUNCH_S
     CK_STEP_LAUNCH();
     // the heavy tail (clumps, hash-collision cells), one warp per deferred particle; exits at once when empty
-    launch_step(h, k_density_heavy, h->num_sms * 4, HEAVY_THREADS, 0, s, h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
-                h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->tile_claim, h->tile_claim + h->cap / 32 + 1, h->ctr);
+    launch_step(h, k_density_heavy, h->num_sms * h->heavy_blocks, HEAVY_THREADS, 0, s, h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
+                h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->tile_claim, h->tile_claim + h->cap / CLUMP_ROWS + 1, h->ctr);
     CK_STEP_LAUNCH();
     return SPH_OK;
 }
@@ -413,9 +414,9 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
         h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt,              \
         h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part)
 #define LAUNCH_FH(M)                                                                                              \
-    launch_step(h, k_forces_heavy<M>, h->num_sms * 4, HEAVY_THREADS, 0, s, h->pos[in], h->vel[in], n, h->gd, h->cells, \
+    launch_step(h, k_forces_heavy<M>, h->num_sms * h->heavy_blocks, HEAVY_THREADS, 0, s, h->pos[in], h->vel[in], n, h->gd, h->cells, \
                 h->P, h->ncount, dt, h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map,             \
-                h->tile_claim + h->cap / 32 + 1)
+                h->tile_claim + h->cap / CLUMP_ROWS + 1)
     if (mode == FI_FORCE_ONLY) {
         CK(cudaMemsetAsync(&h->ctr->heavy[1], 0, sizeof(uint32_t), s));  // the step's deferral list is rebuilt
         CK(cudaMemsetAsync(&h->ctr->clump_rows[1], 0, sizeof(uint32_t), s));
@@ -699,6 +700,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     nh->forces_cfg = 2;  // 128 threads, <= 48 registers: the pass is latency-bound, occupancy wins
     if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_DENSITY_CFG")) nh->density_cfg = std::atoi(e);
+    if (const char *e = std::getenv("SPH_B200_HEAVY_BLOCKS")) nh->heavy_blocks = std::min(std::max(std::atoi(e), 1), HEAVY_BLOCKS_PER_SM);
     if (const char *e = std::getenv("SPH_B200_GRAPH")) nh->graph_enabled = std::atoi(e) != 0;
     if (const char *e = std::getenv("SPH_B200_PDL")) nh->pdl = std::atoi(e) != 0;
     if (const char *e = std::getenv("SPH_B200_EDGE_SCAN")) nh->edge_scan_enabled = std::atoi(e) != 0;
@@ -721,8 +723,8 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     CKC(cudaMalloc(&nh->slab_counts, sizeof(unsigned long long) * (2 * SLAB_MAX_RANKS + 8)));
     CKC(cudaMalloc(&nh->order, sizeof(uint32_t) * cap));
     CKC(cudaMalloc(&nh->map, sizeof(uint32_t) * cap));
-    CKC(cudaMalloc(&nh->tile_claim, sizeof(uint32_t) * 2 * (cap / 32 + 1)));
-    CKC(cudaMemsetAsync(nh->tile_claim, 0, sizeof(uint32_t) * 2 * (cap / 32 + 1), nh->stream));
+    CKC(cudaMalloc(&nh->tile_claim, sizeof(uint32_t) * 2 * (cap / CLUMP_ROWS + 1)));
+    CKC(cudaMemsetAsync(nh->tile_claim, 0, sizeof(uint32_t) * 2 * (cap / CLUMP_ROWS + 1), nh->stream));
     CKC(cudaMalloc(&nh->cells, sizeof(uint32_t) * ((size_t)nh->max_cells + 8)));
     CKC(cudaMalloc(&nh->h16_cells, sizeof(uint32_t) * 65540));
     CKC(cudaMalloc(&nh->const_65536, sizeof(uint32_t)));

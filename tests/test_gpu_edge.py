@@ -193,15 +193,20 @@ def test_clump_takes_the_warp_cooperative_kernels(sph, oracle):
 
 def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
     """nine runs (x offset outer, z offset inner), each the cells y-1, y, y+1 of a column in
-    ascending y, rows of a cell by ascending id; dens = (float)((double)dens + mp * t^3) per accepted row."""
+    ascending y, rows of a cell by ascending id. One-thread kernel: dens = (float)((double)dens + mp * t^3) per
+    accepted row, in that order. Clump rows (tiled phase of the heavy kernel): four double-precision partial sums,
+    part s taking the accepted rows whose rank in their run is s mod 4, combined as (p0 + p2) + (p1 + p3) and
+    rounded to float once. Returns both results, the neighbour count, the longest run and the own cell's size."""
     f = np.float32
     c = tuple(int(v) for v in np.trunc(pos[i] / f(h)).astype(np.int64))
     dens, cnt, longest = f(0), 0, 0
+    part = [np.float64(0)] * 4
     for ox in (-1, 0, 1):
         for oz in (-1, 0, 1):
             run = 0
             for oy in (-1, 0, 1):
                 for j in ids_by_cell.get((c[0] + ox, c[1] + oy, c[2] + oz), ()):
+                    rank = run
                     run += 1
                     if j == i:
                         continue
@@ -209,17 +214,20 @@ def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
                     d2 = f(f(f(d[0] * d[0]) + f(d[1] * d[1])) + f(d[2] * d[2]))
                     if d2 < h2:
                         t = np.float64(f(h2 - d2))
-                        dens = f(np.float64(dens) + np.float64(mp) * ((t * t) * t))
+                        term = np.float64(mp) * ((t * t) * t)
+                        dens = f(np.float64(dens) + term)
+                        part[rank % 4] = part[rank % 4] + term
                         cnt += 1
             longest = max(longest, run)
-    return f(dens + self_dens), cnt, longest, len(ids_by_cell[c])
+    tiled = f(f((part[0] + part[2]) + (part[1] + part[3])) + self_dens)
+    return f(dens + self_dens), tiled, cnt, longest, len(ids_by_cell[c])
 
 
 def test_sums_are_taken_in_the_documented_order(sph):
     """Bit-exact check of the summation order itself, against a numpy restatement: for rows of the one-thread
-    kernel and for clump rows (tiled phase of the heavy kernel), which promise the same sequence. Rows that get
-    a warp of their own (deferred, own cell below the clump threshold) sum by a fixed tree instead: skipped,
-    as are hash-collision neighbourhoods (multiplicities)."""
+    kernel and for clump rows (tiled phase of the heavy kernel). Rows that get a warp of their own (deferred,
+    own cell below the clump threshold) sum by another fixed tree: skipped, as are hash-collision
+    neighbourhoods (multiplicities)."""
     rng = np.random.default_rng(5)
     s = sph.default_settings()
     d = rng.normal(size=(1500, 3))
@@ -251,10 +259,11 @@ def test_sums_are_taken_in_the_documented_order(sph):
     for i in list(rng.choice(1500, 60, replace=False)) + list(1500 + rng.choice(2500, 60, replace=False)):
         if collides(tuple(cells[i])):
             continue
-        want, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(dv.self_dens))
+        seq, tiled, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(dv.self_dens))
         deferred = longest > 96 or cnt > st.nlist_rows
         if deferred and own < 64:
-            continue  # one warp per row: tree sum
+            continue  # one warp per row: another tree
+        want = tiled if deferred else seq
         checked["clump" if deferred else "light"] += 1
         assert got[i].view(np.uint32) == want.view(np.uint32), (i, deferred, cnt, float(got[i]), float(want))
     assert checked["light"] >= 40 and checked["clump"] >= 10, checked
