@@ -83,6 +83,7 @@ struct sph_handle {
     bool rho_pending = false;      // ev_rho has been recorded for this step's force pass to wait on
     bool p2p_clean = false;   // the peer step's device cursors / done-counters are zero (it re-zeroes them itself)
     int forces_cfg = 0, density_cfg = 0;
+    int grid_rows[3] = {4, 2, 1};  // rows per thread of k_cell_hist, k_place, k_order_gather
     int heavy_blocks = HEAVY_BLOCKS_PER_SM;  // blocks per SM of the heavy kernels' persistent grids (SPH_B200_HEAVY_BLOCKS: A/B)
     // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
     // are in the cell order of the last build, i.e. from a slab force step until anything else touches them.
@@ -313,14 +314,30 @@ int build_grid(sph_handle *h)
     cudaStream_t s = h->stream;
     launch_step(h, k_plan_zero, h->num_sms * 8, GRID_THREADS, 0, s, h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
     CK_STEP_LAUNCH();
-    launch_step(h, k_cell_hist, blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s, h->pos[h->cur], n, h->P.h, h->gd, h->cells,
-                h->cell_rank, h->ctr);
+    // Rows per thread of the three latency-bound build kernels (SPH_B200_GRID_CFG="hist,place,gather" for A/B: same bits)
+#define LAUNCH_HIST(R)                                                                                                     \
+    launch_step(h, k_cell_hist<R>, blocks_for(n, R * GRID_THREADS), GRID_THREADS, 0, s, h->pos[h->cur], n, h->P.h, h->gd,  \
+                h->cells, h->cell_rank, h->ctr)
+    switch (h->grid_rows[0]) {
+    case 1: LAUNCH_HIST(1); break;
+    case 2: LAUNCH_HIST(2); break;
+    case 8: LAUNCH_HIST(8); break;
+    default: LAUNCH_HIST(4); break;
+    }
+#undef LAUNCH_HIST
     CK_STEP_LAUNCH();
     launch_step(h, k_scan_exclusive, h->num_sms * 4, SCAN_THREADS, 0, s, h->cells, &h->gd->ncells, h->tile_state,
                 &h->ctr->ticket, &h->ctr->epoch);
     CK_STEP_LAUNCH();
-    launch_step(h, k_place, blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s, h->cell_rank, h->pos[h->cur], n, h->cells, h->slot,
-                h->gd, h->slab_mode ? h->ctr : nullptr, h->slab_lo, h->slab_hi);
+#define LAUNCH_PLACE(R)                                                                                                    \
+    launch_step(h, k_place<R>, blocks_for(n, R * GRID_THREADS), GRID_THREADS, 0, s, h->cell_rank, h->pos[h->cur], n, h->cells, \
+                h->slot, h->gd, h->slab_mode ? h->ctr : nullptr, h->slab_lo, h->slab_hi)
+    switch (h->grid_rows[1]) {
+    case 1: LAUNCH_PLACE(1); break;
+    case 4: LAUNCH_PLACE(4); break;
+    default: LAUNCH_PLACE(2); break;
+    }
+#undef LAUNCH_PLACE
     CK_STEP_LAUNCH();
     uint32_t n_sorted = n;
     const uint32_t *n_dev = nullptr;
@@ -338,9 +355,17 @@ int build_grid(sph_handle *h)
         }
     }
     if (n_sorted) {
-        launch_step(h, k_order_gather, blocks_for(n_sorted, GRID_THREADS), GRID_THREADS, 0, s,
-                    h->slot, h->cell_rank, n_sorted, n_dev, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1],
-                    h->vel[h->cur ^ 1], h->hash16, h->slab_mode ? h->inverse : nullptr);
+#define LAUNCH_GATHER(F, R)                                                                                                \
+    launch_step(h, k_order_gather<F, R>, blocks_for(n_sorted, R * GRID_THREADS), GRID_THREADS, 0, s, h->slot, h->cell_rank,   \
+                n_sorted, n_dev, h->cells, h->P.h, h->pos[h->cur], h->vel[h->cur], h->pos[h->cur ^ 1], h->vel[h->cur ^ 1],    \
+                h->hash16, h->slab_mode ? h->inverse : nullptr, h->gd)
+        switch (h->grid_rows[2]) {
+        case 0: LAUNCH_GATHER(false, 1); break;  // cell looked up in cell_rank (round-1 form)
+        case 2: LAUNCH_GATHER(true, 2); break;
+        case 4: LAUNCH_GATHER(true, 4); break;
+        default: LAUNCH_GATHER(true, 1); break;
+        }
+#undef LAUNCH_GATHER
         CK_STEP_LAUNCH();
     }
     h->cur ^= 1;
@@ -587,7 +612,7 @@ int build_hash16_order(sph_handle *h, bool need_map)
                                                 &h->ctr->epoch);
     CK_LAUNCH();
     if (need_map && n) {
-        k_place<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->h16_cells,
+        k_place<1><<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->cell_rank, h->pos[h->cur], n, h->h16_cells,
                                                                    h->slot, nullptr, nullptr, 0, 0);
         CK_LAUNCH();
         k_stable_order<<<blocks_for(n, GRID_THREADS), GRID_THREADS, 0, s>>>(h->slot, h->cell_rank, n, h->h16_cells,
@@ -700,6 +725,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     nh->forces_cfg = 2;  // 128 threads, <= 48 registers: the pass is latency-bound, occupancy wins
     if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_DENSITY_CFG")) nh->density_cfg = std::atoi(e);
+    if (const char *e = std::getenv("SPH_B200_GRID_CFG")) std::sscanf(e, "%d,%d,%d", &nh->grid_rows[0], &nh->grid_rows[1], &nh->grid_rows[2]);
     if (const char *e = std::getenv("SPH_B200_HEAVY_BLOCKS")) nh->heavy_blocks = std::min(std::max(std::atoi(e), 1), HEAVY_BLOCKS_PER_SM);
     if (const char *e = std::getenv("SPH_B200_GRAPH")) nh->graph_enabled = std::atoi(e) != 0;
     if (const char *e = std::getenv("SPH_B200_PDL")) nh->pdl = std::atoi(e) != 0;

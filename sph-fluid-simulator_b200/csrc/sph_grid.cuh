@@ -222,24 +222,42 @@ k_plan_zero(StepCounters *ctr, GridDesc *gd, int parity, uint32_t max_cells, int
 
 // One thread per particle (array is in last step's cell order, so neighbouring threads hit the
 // same or adjacent counters): cell -> grid index -> rank within the cell by atomicAdd.
+// ROWS rows per thread (row i, i + blockDim, ...: loads stay coalesced): the kernel waits on the returning atomics, and
+// a thread that has issued ROWS of them before it needs the first result keeps ROWS times as many in flight.
+template <int ROWS>
 __global__ void __launch_bounds__(GRID_THREADS)
 k_cell_hist(const float4 *__restrict__ pos, uint32_t n, float h, const GridDesc *__restrict__ gd,
             uint32_t *__restrict__ counts, uint2 *__restrict__ cell_rank, StepCounters *ctr)
 {
     pdl_enter();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const uint32_t i0 = blockIdx.x * (blockDim.x * ROWS) + threadIdx.x;
+    if (i0 >= n) return;
     const GridDesc g = *gd;
-    const float4 p = pos[i];
-    if (__float_as_uint(p.w) == W_DROP) {  // migrated away / stale ghost: leaves the arrays here
-        cell_rank[i] = make_uint2(CELL_NONE, 0u);
-        return;
+    float4 p[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+        const uint32_t i = i0 + k * blockDim.x;
+        p[k] = i < n ? pos[i] : make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
     }
-    bool clamped;
-    const uint32_t c = grid_index(g, cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h), clamped);
-    const uint32_t r = atomicAdd(&counts[c], 1u);
-    cell_rank[i] = make_uint2(c, r);
-    if (clamped) atomicAdd(&ctr->clamped, 1u);
+    uint32_t c[ROWS], r[ROWS];
+    uint32_t nclamped = 0;
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+        c[k] = CELL_NONE;  // migrated away / stale ghost: leaves the arrays here
+        r[k] = 0u;
+        if (__float_as_uint(p[k].w) != W_DROP) {
+            bool clamped;
+            c[k] = grid_index(g, cell_of(p[k].x, h), cell_of(p[k].y, h), cell_of(p[k].z, h), clamped);
+            r[k] = atomicAdd(&counts[c[k]], 1u);
+            nclamped += clamped;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+        const uint32_t i = i0 + k * blockDim.x;
+        if (i < n) cell_rank[i] = make_uint2(c[k], r[k]);
+    }
+    if (nclamped) atomicAdd(&ctr->clamped, nclamped);
 }
 
 // ---- single-pass exclusive scan (decoupled look-back) ---------------------------------------
@@ -353,13 +371,14 @@ __global__ void k_scan_arm(uint32_t *ticket, uint32_t *epoch)
 
 // slot[start[cell] + rank] = (source row, particle id). Within a cell the rank came from
 // atomicAdd, so the order inside a cell segment is arbitrary at this point.
+template <int ROWS>
 __global__ void __launch_bounds__(GRID_THREADS)
 k_place(const uint2 *__restrict__ cell_rank, const float4 *__restrict__ pos, uint32_t n,
         const uint32_t *__restrict__ starts, uint2 *__restrict__ slot, const GridDesc *__restrict__ gd,
         StepCounters *publish_rows, int slab_lo, int slab_hi)
 {
     pdl_enter();
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.x * (blockDim.x * ROWS) + threadIdx.x;
     // slab mode: the rows that survive the build (= the scan's end sentinel) are published for the gather
     // kernel and for the host (this used to be a one-thread kernel of its own), and so is the range of
     // sorted rows that cannot have a ghost among their neighbours: the owned rows of the x-layers
@@ -380,10 +399,19 @@ k_place(const uint2 *__restrict__ cell_rank, const float4 *__restrict__ pos, uin
         publish_rows->interior[0] = r0;
         publish_rows->interior[1] = r1;
     }
-    if (i >= n) return;
-    const uint2 cr = cell_rank[i];
-    if (cr.x == CELL_NONE) return;
-    slot[starts[cr.x] + cr.y] = make_uint2(i, __float_as_uint(pos[i].w) & W_ID_MASK);
+    uint2 cr[ROWS];
+    uint32_t w[ROWS], at[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) {
+        const uint32_t r = i + k * blockDim.x;
+        cr[k] = r < n ? cell_rank[r] : make_uint2(CELL_NONE, 0u);
+        w[k] = r < n ? __float_as_uint(pos[r].w) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k) at[k] = cr[k].x != CELL_NONE ? starts[cr[k].x] + cr[k].y : 0u;
+#pragma unroll
+    for (int k = 0; k < ROWS; ++k)
+        if (cr[k].x != CELL_NONE) slot[at[k]] = make_uint2(i + k * blockDim.x, w[k] & W_ID_MASK);
 }
 
 // Canonical order inside every cell segment: ascending particle id (ids are unique). Each slot
@@ -409,31 +437,65 @@ k_stable_order(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_ra
 // Canonical order + gather in one pass: every slot finds its rank by particle id inside its cell
 // segment and moves its row straight to that place (a scatter confined to the cell segment).
 // pos.w (identity) rides along; the hash16 of the start-of-step cell goes to its own column.
+// FROM_POS: the row's cell is recomputed from its position (the row is gathered anyway, and both gathers are issued
+// as soon as the source row is known) instead of being looked up in cell_rank: one dependent load and 8 bytes per
+// row less in a kernel that is a chain of dependent loads.
+template <bool FROM_POS, int ROWS>
 __global__ void __launch_bounds__(GRID_THREADS)
 k_order_gather(const uint2 *__restrict__ slot, const uint2 *__restrict__ cell_rank, uint32_t n_bound,
                const uint32_t *__restrict__ n_sorted_dev, const uint32_t *__restrict__ starts, float h,
                const float4 *__restrict__ pos_in, const float4 *__restrict__ vel_in, float4 *__restrict__ pos_out,
-               float4 *__restrict__ vel_out, uint32_t *__restrict__ hash_out, uint32_t *__restrict__ inverse)
+               float4 *__restrict__ vel_out, uint32_t *__restrict__ hash_out, uint32_t *__restrict__ inverse,
+               const GridDesc *__restrict__ gd)
 {
     pdl_enter();
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_bound) return;
+    const uint32_t d0 = blockIdx.x * (blockDim.x * ROWS) + threadIdx.x;
+    if (d0 >= n_bound) return;
     // Sync-free slab mode: the host only knows an upper bound of the surviving rows; the exact
     // count is on the device. Rows past it become dropped rows, which every later kernel skips.
-    if (n_sorted_dev && d >= *n_sorted_dev) {
-        pos_out[d] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
-        return;
+    const uint32_t n_sorted = n_sorted_dev ? min(*n_sorted_dev, n_bound) : n_bound;
+    bool live[ROWS];
+    uint2 me[ROWS];
+    float4 p[ROWS], v[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const uint32_t d = d0 + r * blockDim.x;
+        live[r] = d < n_sorted;
+        if (!live[r] && d < n_bound) pos_out[d] = make_float4(0.f, 0.f, 0.f, __uint_as_float(W_DROP));
+        me[r] = live[r] ? slot[d] : make_uint2(0u, 0u);
     }
-    const uint2 me = slot[d];
-    const uint32_t c = cell_rank[me.x].x;
-    const uint32_t s = starts[c], e = starts[c + 1];
-    uint32_t k = s;
-    for (uint32_t t = s; t < e; ++t) k += (slot[t].y < me.y);
-    const float4 p = pos_in[me.x];
-    pos_out[k] = p;
-    vel_out[k] = vel_in[me.x];
-    hash_out[k] = hash16_of(cell_of(p.x, h), cell_of(p.y, h), cell_of(p.z, h));
-    if (inverse) inverse[me.x] = k;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {  // both gathers are issued as soon as the source row is known
+        p[r] = live[r] ? pos_in[me[r].x] : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[r] = live[r] ? vel_in[me[r].x] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t s[ROWS], e[ROWS], hsh[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int cx = cell_of(p[r].x, h), cy = cell_of(p[r].y, h), cz = cell_of(p[r].z, h);
+        hsh[r] = hash16_of(cx, cy, cz);
+        uint32_t c = 0;
+        if (live[r]) {
+            if (FROM_POS) {
+                bool clamped;
+                c = grid_index(*gd, cx, cy, cz, clamped);  // what k_cell_hist computed for this row
+            } else {
+                c = cell_rank[me[r].x].x;
+            }
+        }
+        s[r] = live[r] ? starts[c] : 0u;
+        e[r] = live[r] ? starts[c + 1] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (!live[r]) continue;
+        uint32_t k = s[r];
+        for (uint32_t t = s[r]; t < e[r]; ++t) k += (slot[t].y < me[r].y);
+        pos_out[k] = p[r];
+        vel_out[k] = v[r];
+        hash_out[k] = hsh[r];
+        if (inverse) inverse[me[r].x] = k;
+    }
 }
 
 }  // namespace sphb

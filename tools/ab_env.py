@@ -26,9 +26,11 @@ def run(name, make, settle, steps, reps=5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream); sim.step(steps); e1.record(stream); sim.sync()
             ms.append(e0.elapsed_time(e1) / steps)
+        sim.enable_pass_timing(True); sim.step(20); pt = sim.pass_times(); sim.enable_pass_timing(False)
         d = sim.download(S.ORDER_ID, fields=("pos", "vel", "density"))
         dig = hashlib.sha1(d["pos"].tobytes() + d["vel"].tobytes() + d["density"].tobytes()).hexdigest()[:16]
-        out[v] = dict(ms_per_step=sorted(ms)[len(ms) // 2], all=[round(m, 5) for m in ms], digest=dig)
+        out[v] = dict(ms_per_step=sorted(ms)[len(ms) // 2], all=[round(m, 5) for m in ms], digest=dig,
+                      pass_ms={k: round(x, 4) for k, x in pt.items() if k != "steps"})
         sim.close()
     digs = {o["digest"] for o in out.values()}
     print(json.dumps({"workload": name, "var": var, "results": out, "bit_identical": len(digs) == 1}), flush=True)
