@@ -434,8 +434,9 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
     cudaStream_t s = h->stream;
     // FI_FORCE_ONLY reads the start-of-step rows, which after the step live in the non-current buffers
     const int in = mode == FI_FORCE_ONLY ? (h->cur ^ 1) : h->cur;
-#define LAUNCH_FI(T, B, M)                                                                                       \
-    launch_step(h, k_forces_integrate<T, B, M>, blocks_for(n, T), T, 0, s,                                       \
+#define LAUNCH_FI(T, B, M) LAUNCH_FIP(T, B, M, true, 1)
+#define LAUNCH_FIP(T, B, M, PK, PIPE)                                                                            \
+    launch_step(h, k_forces_integrate<T, B, M, PK, PIPE>, blocks_for(n, T), T, 0, s,                             \
         h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt,              \
         h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part)
 #define LAUNCH_FH(M)                                                                                              \
@@ -446,9 +447,9 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
         CK(cudaMemsetAsync(&h->ctr->heavy[1], 0, sizeof(uint32_t), s));  // the step's deferral list is rebuilt
         CK(cudaMemsetAsync(&h->ctr->clump_rows[1], 0, sizeof(uint32_t), s));
         CK(cudaMemsetAsync(&h->ctr->clump_ticket[1], 0, 2 * sizeof(uint32_t), s));  // force list and tile tickets
-        LAUNCH_FI(128, 10, FI_FORCE_ONLY);
+        LAUNCH_FI(128, 12, FI_FORCE_ONLY);
     } else if (mode == FI_STEP_WRITE_FORCE) {
-        LAUNCH_FI(128, 10, FI_STEP_WRITE_FORCE);
+        LAUNCH_FI(128, 12, FI_STEP_WRITE_FORCE);
     } else {
 #define LAUNCH_FT(T, B, CAPR)                                                                                     \
     do {                                                                                                         \
@@ -463,19 +464,21 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
     } while (0)
         switch ((part != 0 && h->forces_cfg == 6) ? 2 : h->forces_cfg) {  // the tile-staged variant has no split form
         case 6: LAUNCH_FT(128, 5, 1408); break;  // shared-memory staged neighbourhoods: measured 2-4x slower
-        case 7:  // the scalar form of the force terms (A/B against the packed default: same bits)
-            launch_step(h, k_forces_integrate<128, 10, FI_STEP, false>, blocks_for(n, 128), 128, 0, s,
-                h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt, h->pos[in ^ 1],
-                h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part);
-            break;
+        case 7: LAUNCH_FIP(128, 10, FI_STEP, false, 1); break;  // the scalar form of the force terms (A/B against the packed default: same bits)
+        case 8: LAUNCH_FIP(128, 10, FI_STEP, true, 0); break;   // round-2-start form: no software pipeline, 48 registers
+        case 9: LAUNCH_FIP(128, 10, FI_STEP, true, 1); break;
+        case 10: LAUNCH_FIP(128, 10, FI_STEP, true, 2); break;  // next neighbour's rows in flight too
+        case 11: LAUNCH_FIP(128, 12, FI_STEP, true, 2); break;
+        case 12: LAUNCH_FIP(128, 8, FI_STEP, true, 2); break;
         case 1: LAUNCH_FI(128, 8, FI_STEP); break;
         case 3: LAUNCH_FI(64, 16, FI_STEP); break;
         case 4: LAUNCH_FI(256, 4, FI_STEP); break;
-        case 5: LAUNCH_FI(128, 12, FI_STEP); break;
-        default: LAUNCH_FI(128, 10, FI_STEP); break;
+        case 5: LAUNCH_FI(128, 16, FI_STEP); break;
+        default: LAUNCH_FI(128, 12, FI_STEP); break;  // list entry one neighbour ahead, 40 registers
         }
     }
 #undef LAUNCH_FI
+#undef LAUNCH_FIP
     CK_STEP_LAUNCH();
     if (part == 1) return SPH_OK;  // the rows outside the interior range follow in a second launch, which completes the pass
     if (mode == FI_FORCE_ONLY) LAUNCH_FH(FI_FORCE_ONLY);
