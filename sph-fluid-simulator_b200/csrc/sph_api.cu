@@ -83,6 +83,7 @@ struct sph_handle {
     bool rho_pending = false;      // ev_rho has been recorded for this step's force pass to wait on
     bool p2p_clean = false;   // the peer step's device cursors / done-counters are zero (it re-zeroes them itself)
     int forces_cfg = 0, density_cfg = 0;
+    int scan_blocks = 8;  // blocks per SM of the scan's persistent grid (SPH_B200_SCAN_BLOCKS: A/B)
     int grid_rows[3] = {4, 2, 1};  // rows per thread of k_cell_hist, k_place, k_order_gather
     int heavy_blocks = HEAVY_BLOCKS_PER_SM;  // blocks per SM of the heavy kernels' persistent grids (SPH_B200_HEAVY_BLOCKS: A/B)
     // Sync-free slab steps scan only the edge x-layers (sph_slab.cuh, "edge scans"): valid while the rows
@@ -326,7 +327,7 @@ int build_grid(sph_handle *h)
     }
 #undef LAUNCH_HIST
     CK_STEP_LAUNCH();
-    launch_step(h, k_scan_exclusive, h->num_sms * 4, SCAN_THREADS, 0, s, h->cells, &h->gd->ncells, h->tile_state,
+    launch_step(h, k_scan_exclusive, h->num_sms * h->scan_blocks, SCAN_THREADS, 0, s, h->cells, &h->gd->ncells, h->tile_state,
                 &h->ctr->ticket, &h->ctr->epoch);
     CK_STEP_LAUNCH();
 #define LAUNCH_PLACE(R)                                                                                                    \
@@ -728,6 +729,7 @@ int sph_create(const sph_settings *s, uint64_t capacity, int device, sph_handle 
     nh->forces_cfg = 2;  // 128 threads, <= 48 registers: the pass is latency-bound, occupancy wins
     if (const char *e = std::getenv("SPH_B200_FORCES_CFG")) nh->forces_cfg = std::atoi(e);
     if (const char *e = std::getenv("SPH_B200_DENSITY_CFG")) nh->density_cfg = std::atoi(e);
+    if (const char *e = std::getenv("SPH_B200_SCAN_BLOCKS")) nh->scan_blocks = std::min(std::max(std::atoi(e), 1), 8);
     if (const char *e = std::getenv("SPH_B200_GRID_CFG")) std::sscanf(e, "%d,%d,%d", &nh->grid_rows[0], &nh->grid_rows[1], &nh->grid_rows[2]);
     if (const char *e = std::getenv("SPH_B200_HEAVY_BLOCKS")) nh->heavy_blocks = std::min(std::max(std::atoi(e), 1), HEAVY_BLOCKS_PER_SM);
     if (const char *e = std::getenv("SPH_B200_GRAPH")) nh->graph_enabled = std::atoi(e) != 0;
