@@ -170,6 +170,13 @@ int fail(sph_handle *h, int code, const char *fmt, ...)
 
 inline unsigned blocks_for(uint64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
+// Blocks of a persistent grid: per_sm blocks on every SM, but no more than the work can use (a 3 375-particle cube
+// does not need 1 184 blocks that look at a counter and leave: every one of them is launch latency of a 30 us step).
+inline unsigned persistent_blocks(const sph_handle *h, int per_sm, uint64_t useful)
+{
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)h->num_sms * per_sm, useful));
+}
+
 // Launch of a step kernel with programmatic stream serialization (pdl_enter in sph_device.cuh): the kernel's
 // blocks may become resident while the kernel in front of it drains and wait on the device for its completion,
 // which would hide launch latency between the nine kernels of a step. A captured step keeps these as
@@ -313,7 +320,7 @@ int build_grid(sph_handle *h)
     h->edge_ok = false;  // rows move; a slab force step declares them ordered again
     const uint32_t n = (uint32_t)h->n;
     cudaStream_t s = h->stream;
-    launch_step(h, k_plan_zero, h->num_sms * 8, GRID_THREADS, 0, s, h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
+    launch_step(h, k_plan_zero, persistent_blocks(h, 8, (uint64_t)h->max_cells / (4 * GRID_THREADS) + 1), GRID_THREADS, 0, s, h->ctr, h->gd, h->parity, h->max_cells, h->bbox_expand, h->cells);
     CK_STEP_LAUNCH();
     // Rows per thread of the three latency-bound build kernels (SPH_B200_GRID_CFG="hist,place,gather" for A/B: same bits)
 #define LAUNCH_HIST(R)                                                                                                     \
@@ -327,7 +334,7 @@ int build_grid(sph_handle *h)
     }
 #undef LAUNCH_HIST
     CK_STEP_LAUNCH();
-    launch_step(h, k_scan_exclusive, h->num_sms * h->scan_blocks, SCAN_THREADS, 0, s, h->cells, &h->gd->ncells, h->tile_state,
+    launch_step(h, k_scan_exclusive, persistent_blocks(h, h->scan_blocks, (uint64_t)h->max_cells / SCAN_TILE + 2), SCAN_THREADS, 0, s, h->cells, &h->gd->ncells, h->tile_state,
                 &h->ctr->ticket, &h->ctr->epoch);
     CK_STEP_LAUNCH();
 #define LAUNCH_PLACE(R)                                                                                                    \
@@ -420,7 +427,7 @@ int launch_density(sph_handle *h, uint32_t n)
 #undef LAUNCH_S
     CK_STEP_LAUNCH();
     // the heavy tail (clumps, hash-collision cells), one warp per deferred particle; exits at once when empty
-    launch_step(h, k_density_heavy, h->num_sms * h->heavy_blocks, HEAVY_THREADS, 0, s, h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
+    launch_step(h, k_density_heavy, persistent_blocks(h, h->heavy_blocks, n / 64 + 8), HEAVY_THREADS, 0, s, h->pos[h->cur], n, h->gd, h->cells, h->P, h->vel[h->cur],
                 h->nlist, h->ncount, (uint32_t)h->cap, h->order, h->tile_claim, h->tile_claim + h->cap / CLUMP_ROWS + 1, h->ctr);
     CK_STEP_LAUNCH();
     return SPH_OK;
@@ -441,7 +448,7 @@ int launch_forces_integrate(sph_handle *h, uint32_t n, float dt, int mode, int p
         h->pos[in], h->vel[in], n, h->gd, h->cells, h->P, h->nlist, h->ncount, (uint32_t)h->cap, dt,              \
         h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map, part)
 #define LAUNCH_FH(M)                                                                                              \
-    launch_step(h, k_forces_heavy<M>, h->num_sms * h->heavy_blocks, HEAVY_THREADS, 0, s, h->pos[in], h->vel[in], n, h->gd, h->cells, \
+    launch_step(h, k_forces_heavy<M>, persistent_blocks(h, h->heavy_blocks, n / 64 + 8), HEAVY_THREADS, 0, s, h->pos[in], h->vel[in], n, h->gd, h->cells, \
                 h->P, h->ncount, dt, h->pos[in ^ 1], h->vel[in ^ 1], h->force, h->ctr, h->parity ^ 1, h->map,             \
                 h->tile_claim + h->cap / CLUMP_ROWS + 1)
     if (mode == FI_FORCE_ONLY) {

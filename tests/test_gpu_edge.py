@@ -155,11 +155,25 @@ def test_ids_with_the_ghost_bit_are_refused(sph):
     sim.close()
 
 
-def test_clump_takes_the_warp_cooperative_kernels(sph, oracle):
+@pytest.fixture(params=["64", "0"], ids=["tiles", "warp-per-row"])
+def clump_cell(request):
+    """SPH_B200_CLUMP_CELL for the handles the test creates: 64 (the default) — deferred rows of crowded cells are
+    served an 8-row tile at a time; 0 — every deferred row gets a warp of its own (heavy tail)."""
+    old = os.environ.get("SPH_B200_CLUMP_CELL")
+    os.environ["SPH_B200_CLUMP_CELL"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["SPH_B200_CLUMP_CELL"]
+    else:
+        os.environ["SPH_B200_CLUMP_CELL"] = old
+
+
+def test_clump_takes_the_warp_cooperative_kernels(sph, oracle, clump_cell):
     """A clump (hundreds of neighbours per particle, what the reference's fluid collapses into after
     ~2000 steps) overflows the per-particle neighbour list and the per-run budget of the one-thread
-    kernels: those particles are deferred to kernels that put a warp on each. Same neighbour
-    multisets, same tolerances, and the same bits every time."""
+    kernels: those particles are deferred to the heavy kernels (one warp per row, or — rows of crowded
+    cells — a tile of rows on the candidates they share). Same neighbour multisets, same tolerances, and
+    the same bits every time, for either class."""
     rng = np.random.default_rng(5)
     s = sph.default_settings()
     d = rng.normal(size=(1500, 3))
