@@ -77,8 +77,9 @@ typedef struct sph_stats {
     double mean_density;      /* mean of the last step's density */
     double max_density;
     double kinetic_energy;    /* 0.5 * mass * sum |v|^2 */
-    uint64_t deferred_density; /* particles the last step handed to the warp-cooperative density kernel */
-    uint64_t deferred_forces;  /* ... and to the warp-cooperative force kernel */
+    uint64_t deferred_density; /* particles the last step handed to the heavy density kernel (one warp per row, or - rows of
+                                  crowded cells - an 8-row tile at a time) */
+    uint64_t deferred_forces;  /* ... and to the heavy force kernel */
     uint64_t nlist_rows;       /* rows of the per-particle neighbour list; particles with more neighbours are deferred */
 } sph_stats;
 
