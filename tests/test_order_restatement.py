@@ -1,0 +1,40 @@
+"""CPU: the numpy restatement of the library's summation orders (tests/test_gpu_edge.py uses it to check the CUDA
+path bit for bit) is itself checked here against the oracle: same neighbour counts, and densities within the
+tolerance that a change of summation order is allowed. This pins the checker on a box without a
+GPU: what the GPU test then proves is the ORDER, on top of physics already proven to be the reference's."""
+import numpy as np
+
+from conftest import by_id
+from test_gpu_edge import _density_in_documented_order
+
+
+def test_restated_sums_are_the_reference_physics(oracle):
+    rng = np.random.default_rng(5)
+    s = oracle.settings()
+    d = rng.normal(size=(1500, 3))
+    d *= (0.25 * rng.uniform(0, 1, (1500, 1)) ** (1 / 3)) / np.linalg.norm(d, axis=1, keepdims=True)
+    pos = np.concatenate([d + [1.0, 1.0, 1.0], rng.uniform([-3, 0.2, -3], [3, 3, 3], (2500, 3))]).astype(np.float32)
+    vel = np.zeros_like(pos)
+    want = by_id(oracle.step(s, 0.003, pos, vel))
+    order, ocounts, _, _, _ = oracle.neighbor_lists(s, pos)
+    counts = ocounts[np.argsort(order)]
+    f = np.float32
+    h, h2, mp = f(s.h), f(s.h2), f(s.massPoly6Product)
+    cells = np.trunc(pos / h).astype(np.int64)
+    ids_by_cell = {}
+    for j, c in enumerate(map(tuple, cells)):
+        ids_by_cell.setdefault(c, []).append(j)
+    M = (73856093, 19349663, 83492791)
+    checked = 0
+    for i in list(rng.choice(1500, 25, replace=False)) + list(1500 + rng.choice(2500, 25, replace=False)):
+        c = tuple(cells[i])
+        hs = [((c[0] + x) * M[0] ^ (c[1] + y) * M[1] ^ (c[2] + z) * M[2]) & 0xFFFF
+              for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
+        if len(set(hs)) < 27:
+            continue  # hash-collision neighbourhood: the reference counts some neighbours twice
+        seq, tiled, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(s.selfDens))
+        assert cnt == counts[i], (i, cnt, counts[i])
+        for got in (seq, tiled):
+            assert abs(float(got) - float(want["density"][i])) <= 1e-5 * float(want["density"][i]), (i, got, want["density"][i])
+        checked += 1
+    assert checked >= 40
