@@ -237,6 +237,55 @@ def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
     return f(dens + self_dens), tiled, cnt, longest, len(ids_by_cell[c])
 
 
+def _force_in_documented_order(pos, vel, rho, ids_by_cell, i, K):
+    """The force terms of src/sph.cpp:110-121 in float32, operation by operation, accumulated in the documented
+    orders (see _density_in_documented_order): the one-thread kernel's running sum, and the tiled phase's four
+    partial sums by rank in the run combined as (p0 + p2) + (p1 + p3). rho: density of every particle (by id).
+    K: dict of float32 constants h, h2, mass, gas, rest, visc_mass, spiky_grad, spiky_lap."""
+    f = np.float32
+    c = tuple(int(v) for v in np.trunc(pos[i] / K["h"]).astype(np.int64))
+    pres_i = f(K["gas"] * f(rho[i] - K["rest"]))
+    seq = np.zeros(3, f)
+    part = np.zeros((4, 3), f)
+
+    def add(acc, t):
+        for a in range(3):
+            acc[a] = f(acc[a] + t[a])
+
+    with np.errstate(all="ignore"):
+        for ox in (-1, 0, 1):
+            for oz in (-1, 0, 1):
+                run = 0
+                for oy in (-1, 0, 1):
+                    for j in ids_by_cell.get((c[0] + ox, c[1] + oy, c[2] + oz), ()):
+                        rank = run
+                        run += 1
+                        if j == i:
+                            continue
+                        d = pos[j] - pos[i]
+                        d2 = f(f(f(d[0] * d[0]) + f(d[1] * d[1])) + f(d[2] * d[2]))
+                        if not d2 < K["h2"]:
+                            continue
+                        dist = np.sqrt(d2, dtype=f)
+                        inv = f(f(1.0) / dist)
+                        psum = f(pres_i + f(K["gas"] * f(rho[j] - K["rest"])))
+                        den = f(f(2.0) * rho[j])
+                        hd = f(K["h"] - dist)
+                        w2 = f(hd * hd)
+                        P = np.zeros(3, f)
+                        V = np.zeros(3, f)
+                        for a in range(3):
+                            n = f(d[a] * inv)
+                            P[a] = f(f(f(f(f(f(-n) * K["mass"]) * psum) / den) * K["spiky_grad"]) * w2)
+                            u = f(vel[j][a] - vel[i][a])
+                            V[a] = f(f(f(K["visc_mass"] * f(u / rho[j])) * K["spiky_lap"]) * hd)
+                        for acc in (seq, part[rank % 4]):
+                            add(acc, P)
+                            add(acc, V)
+    tiled = np.array([f(f(part[0][a] + part[2][a]) + f(part[1][a] + part[3][a])) for a in range(3)], f)
+    return seq, tiled
+
+
 def test_sums_are_taken_in_the_documented_order(sph):
     """Bit-exact check of the summation order itself, against a numpy restatement: for rows of the one-thread
     kernel and for clump rows (tiled phase of the heavy kernel). Rows that get a warp of their own (deferred,
@@ -247,17 +296,20 @@ def test_sums_are_taken_in_the_documented_order(sph):
     d = rng.normal(size=(1500, 3))
     d *= (0.25 * rng.uniform(0, 1, (1500, 1)) ** (1 / 3)) / np.linalg.norm(d, axis=1, keepdims=True)
     pos = np.concatenate([d + [1.0, 1.0, 1.0], rng.uniform([-3, 0.2, -3], [3, 3, 3], (2500, 3))]).astype(np.float32)
-    vel = np.zeros_like(pos)
+    vel = rng.normal(0, 0.5, pos.shape).astype(np.float32)
     sim = sph.Sim(s, capacity=len(pos))
     sim.upload(pos, vel)
     sim.step(1)
-    got = sim.download(sph.ORDER_ID, fields=("density",))["density"]
+    out = sim.download(sph.ORDER_ID, fields=("density", "force"))
+    got, got_force = out["density"], out["force"]
     st = sim.stats()
     sim.close()
     assert st.deferred_density >= 1400
     dv = sph.derive(s)
     f = np.float32
     h, h2, mp = f(s.h), f(dv.h2), f(f(s.mass) * f(dv.poly6))
+    K = dict(h=h, h2=h2, mass=f(s.mass), gas=f(s.gas_constant), rest=f(s.rest_density), visc_mass=f(f(s.viscosity) * f(s.mass)),
+             spiky_grad=f(dv.spiky_grad), spiky_lap=f(dv.spiky_lap))
     cells = np.trunc(pos / h).astype(np.int64)
     ids_by_cell = {}
     for j, c in enumerate(map(tuple, cells)):
@@ -280,6 +332,11 @@ def test_sums_are_taken_in_the_documented_order(sph):
         want = tiled if deferred else seq
         checked["clump" if deferred else "light"] += 1
         assert got[i].view(np.uint32) == want.view(np.uint32), (i, deferred, cnt, float(got[i]), float(want))
+        # the force sums in the same orders, from the densities the GPU computed (compared bit for bit above for
+        # this row; its neighbours' enter as they are)
+        fseq, ftiled = _force_in_documented_order(pos, vel, got, ids_by_cell, i, K)
+        fwant = ftiled if deferred else fseq
+        assert np.array_equal(got_force[i].view(np.uint32), fwant.view(np.uint32)), (i, deferred, got_force[i], fwant)
     assert checked["light"] >= 40 and checked["clump"] >= 10, checked
 
 

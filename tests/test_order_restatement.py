@@ -5,7 +5,7 @@ GPU: what the GPU test then proves is the ORDER, on top of physics already prove
 import numpy as np
 
 from conftest import by_id
-from test_gpu_edge import _density_in_documented_order
+from test_gpu_edge import _density_in_documented_order, _force_in_documented_order
 
 
 def test_restated_sums_are_the_reference_physics(oracle):
@@ -14,7 +14,7 @@ def test_restated_sums_are_the_reference_physics(oracle):
     d = rng.normal(size=(1500, 3))
     d *= (0.25 * rng.uniform(0, 1, (1500, 1)) ** (1 / 3)) / np.linalg.norm(d, axis=1, keepdims=True)
     pos = np.concatenate([d + [1.0, 1.0, 1.0], rng.uniform([-3, 0.2, -3], [3, 3, 3], (2500, 3))]).astype(np.float32)
-    vel = np.zeros_like(pos)
+    vel = rng.normal(0, 0.5, pos.shape).astype(np.float32)
     want = by_id(oracle.step(s, 0.003, pos, vel))
     order, ocounts, _, _, _ = oracle.neighbor_lists(s, pos)
     counts = ocounts[np.argsort(order)]
@@ -25,6 +25,9 @@ def test_restated_sums_are_the_reference_physics(oracle):
     for j, c in enumerate(map(tuple, cells)):
         ids_by_cell.setdefault(c, []).append(j)
     M = (73856093, 19349663, 83492791)
+    K = dict(h=h, h2=h2, mass=f(s.mass), gas=f(s.gasConstant), rest=f(s.restDensity), visc_mass=f(f(s.viscosity) * f(s.mass)),
+             spiky_grad=f(s.spikyGrad), spiky_lap=f(s.spikyLap))
+    fmed = float(np.median(np.linalg.norm(want["force"][:1500], axis=1)))
     checked = 0
     for i in list(rng.choice(1500, 25, replace=False)) + list(1500 + rng.choice(2500, 25, replace=False)):
         c = tuple(cells[i])
@@ -36,5 +39,10 @@ def test_restated_sums_are_the_reference_physics(oracle):
         assert cnt == counts[i], (i, cnt, counts[i])
         for got in (seq, tiled):
             assert abs(float(got) - float(want["density"][i])) <= 1e-5 * float(want["density"][i]), (i, got, want["density"][i])
+        fseq, ftiled = _force_in_documented_order(pos, vel, want["density"], ids_by_cell, i, K)
+        fw = want["force"][i]
+        scale = max(float(np.linalg.norm(fw)), fmed)
+        for gotf in (fseq, ftiled):
+            assert float(np.linalg.norm(gotf - fw)) <= 1e-3 * scale, (i, gotf, fw)
         checked += 1
     assert checked >= 40
