@@ -207,14 +207,17 @@ def test_clump_takes_the_warp_cooperative_kernels(sph, oracle, clump_cell):
 
 def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
     """nine runs (x offset outer, z offset inner), each the cells y-1, y, y+1 of a column in
-    ascending y, rows of a cell by ascending id. One-thread kernel: dens = (float)((double)dens + mp * t^3) per
-    accepted row, in that order. Clump rows (tiled phase of the heavy kernel): four double-precision partial sums,
-    part s taking the accepted rows whose rank in their run is s mod 4, combined as (p0 + p2) + (p1 + p3) and
-    rounded to float once. Returns both results, the neighbour count, the longest run and the own cell's size."""
+    ascending y, rows of a cell by ascending id. One-thread kernel ("seq"): dens = (float)((double)dens + mp * t^3)
+    per accepted row, in that order. Clump rows ("tiled", tiled phase of the heavy kernel): four double-precision
+    partial sums, part s taking the accepted rows whose rank in their run is s mod 4, combined as
+    (p0 + p2) + (p1 + p3) and rounded to float once. One warp per row ("warp"): 32 double-precision partial sums by
+    rank mod 32, combined by an xor butterfly, rounded once. Returns the three results, the neighbour count, the
+    longest run and the own cell's size."""
     f = np.float32
     c = tuple(int(v) for v in np.trunc(pos[i] / f(h)).astype(np.int64))
     dens, cnt, longest = f(0), 0, 0
     part = [np.float64(0)] * 4
+    lanes = np.zeros(32, np.float64)  # one warp per row: lane (rank in run) % 32, then a butterfly over the lanes
     for ox in (-1, 0, 1):
         for oz in (-1, 0, 1):
             run = 0
@@ -231,22 +234,28 @@ def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
                         term = np.float64(mp) * ((t * t) * t)
                         dens = f(np.float64(dens) + term)
                         part[rank % 4] = part[rank % 4] + term
+                        lanes[rank % 32] = lanes[rank % 32] + term
                         cnt += 1
             longest = max(longest, run)
     tiled = f(f((part[0] + part[2]) + (part[1] + part[3])) + self_dens)
-    return f(dens + self_dens), tiled, cnt, longest, len(ids_by_cell[c])
+    for o in (16, 8, 4, 2, 1):
+        lanes = lanes + lanes[np.arange(32) ^ o]
+    warp = f(f(lanes[0]) + self_dens)
+    return {"seq": f(dens + self_dens), "tiled": tiled, "warp": warp}, cnt, longest, len(ids_by_cell[c])
 
 
 def _force_in_documented_order(pos, vel, rho, ids_by_cell, i, K):
     """The force terms of src/sph.cpp:110-121 in float32, operation by operation, accumulated in the documented
-    orders (see _density_in_documented_order): the one-thread kernel's running sum, and the tiled phase's four
-    partial sums by rank in the run combined as (p0 + p2) + (p1 + p3). rho: density of every particle (by id).
+    orders (see _density_in_documented_order): the one-thread kernel's running sum, the tiled phase's four
+    partial sums by rank in the run combined as (p0 + p2) + (p1 + p3), and the 32 per-lane sums of a row that has a
+    warp of its own, combined by the butterfly. rho: density of every particle (by id).
     K: dict of float32 constants h, h2, mass, gas, rest, visc_mass, spiky_grad, spiky_lap."""
     f = np.float32
     c = tuple(int(v) for v in np.trunc(pos[i] / K["h"]).astype(np.int64))
     pres_i = f(K["gas"] * f(rho[i] - K["rest"]))
     seq = np.zeros(3, f)
     part = np.zeros((4, 3), f)
+    lanes = np.zeros((32, 3), f)
 
     def add(acc, t):
         for a in range(3):
@@ -279,18 +288,19 @@ def _force_in_documented_order(pos, vel, rho, ids_by_cell, i, K):
                             P[a] = f(f(f(f(f(f(-n) * K["mass"]) * psum) / den) * K["spiky_grad"]) * w2)
                             u = f(vel[j][a] - vel[i][a])
                             V[a] = f(f(f(K["visc_mass"] * f(u / rho[j])) * K["spiky_lap"]) * hd)
-                        for acc in (seq, part[rank % 4]):
+                        for acc in (seq, part[rank % 4], lanes[rank % 32]):
                             add(acc, P)
                             add(acc, V)
-    tiled = np.array([f(f(part[0][a] + part[2][a]) + f(part[1][a] + part[3][a])) for a in range(3)], f)
-    return seq, tiled
+        tiled = np.array([f(f(part[0][a] + part[2][a]) + f(part[1][a] + part[3][a])) for a in range(3)], f)
+        for o in (16, 8, 4, 2, 1):
+            lanes = (lanes + lanes[np.arange(32) ^ o]).astype(f)
+    return {"seq": seq, "tiled": tiled, "warp": lanes[0].copy()}
 
 
 def test_sums_are_taken_in_the_documented_order(sph):
     """Bit-exact check of the summation order itself, against a numpy restatement: for rows of the one-thread
-    kernel and for clump rows (tiled phase of the heavy kernel). Rows that get a warp of their own (deferred,
-    own cell below the clump threshold) sum by another fixed tree: skipped, as are hash-collision
-    neighbourhoods (multiplicities)."""
+    kernel, for clump rows (tiled phase of the heavy kernel) and for rows that get a warp of their own (deferred,
+    own cell below the clump threshold). Hash-collision neighbourhoods (multiplicities) are skipped."""
     rng = np.random.default_rng(5)
     s = sph.default_settings()
     d = rng.normal(size=(1500, 3))
@@ -321,23 +331,24 @@ def test_sums_are_taken_in_the_documented_order(sph):
               for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
         return len(set(hs)) < 27
 
-    checked = {"light": 0, "clump": 0}
+    checked = {"light": 0, "clump": 0, "warp": 0}
     for i in list(rng.choice(1500, 60, replace=False)) + list(1500 + rng.choice(2500, 60, replace=False)):
         if collides(tuple(cells[i])):
             continue
-        seq, tiled, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(dv.self_dens))
+        dens, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(dv.self_dens))
         deferred = longest > 96 or cnt > st.nlist_rows
-        if deferred and own < 64:
-            continue  # one warp per row: another tree
-        want = tiled if deferred else seq
-        checked["clump" if deferred else "light"] += 1
-        assert got[i].view(np.uint32) == want.view(np.uint32), (i, deferred, cnt, float(got[i]), float(want))
+        # which kernel sums this row: the density pass, then the force pass (a deferred row whose list fits is
+        # back with the one-thread force kernel, which reads the list the heavy kernel wrote in walk order)
+        dclass = "seq" if not deferred else ("tiled" if own >= 64 else "warp")
+        fclass = "tiled" if dclass == "tiled" else ("warp" if cnt > st.nlist_rows else "seq")
+        checked[{"seq": "light", "tiled": "clump", "warp": "warp"}[dclass]] += 1
+        want = dens[dclass]
+        assert got[i].view(np.uint32) == want.view(np.uint32), (i, dclass, cnt, float(got[i]), float(want))
         # the force sums in the same orders, from the densities the GPU computed (compared bit for bit above for
         # this row; its neighbours' enter as they are)
-        fseq, ftiled = _force_in_documented_order(pos, vel, got, ids_by_cell, i, K)
-        fwant = ftiled if deferred else fseq
-        assert np.array_equal(got_force[i].view(np.uint32), fwant.view(np.uint32)), (i, deferred, got_force[i], fwant)
-    assert checked["light"] >= 40 and checked["clump"] >= 10, checked
+        fwant = _force_in_documented_order(pos, vel, got, ids_by_cell, i, K)[fclass]
+        assert np.array_equal(got_force[i].view(np.uint32), fwant.view(np.uint32)), (i, dclass, fclass, got_force[i], fwant)
+    assert checked["light"] >= 40 and checked["clump"] >= 10 and checked["warp"] >= 5, checked
 
 
 def test_captured_steps_replay_the_same_bits():

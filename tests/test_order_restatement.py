@@ -35,14 +35,14 @@ def test_restated_sums_are_the_reference_physics(oracle):
               for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
         if len(set(hs)) < 27:
             continue  # hash-collision neighbourhood: the reference counts some neighbours twice
-        seq, tiled, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(s.selfDens))
+        dens, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(s.selfDens))
         assert cnt == counts[i], (i, cnt, counts[i])
-        for got in (seq, tiled):
+        for got in dens.values():
             assert abs(float(got) - float(want["density"][i])) <= 1e-5 * float(want["density"][i]), (i, got, want["density"][i])
-        fseq, ftiled = _force_in_documented_order(pos, vel, want["density"], ids_by_cell, i, K)
+        forces = _force_in_documented_order(pos, vel, want["density"], ids_by_cell, i, K)
         fw = want["force"][i]
         scale = max(float(np.linalg.norm(fw)), fmed)
-        for gotf in (fseq, ftiled):
+        for gotf in forces.values():
             assert float(np.linalg.norm(gotf - fw)) <= 1e-3 * scale, (i, gotf, fw)
         checked += 1
     assert checked >= 40
