@@ -297,6 +297,31 @@ def _force_in_documented_order(pos, vel, rho, ids_by_cell, i, K):
     return {"seq": seq, "tiled": tiled, "warp": lanes[0].copy()}
 
 
+def _integrate_as_the_reference_does(p, v, F, rho, s):
+    """src/sph.cpp:138-179 in float32: a = F / rho + (0, g, 0); v += a dt; x += v dt; then the five wall tests in
+    order, each on the already-updated value."""
+    f = np.float32
+    h, dt, box, el, off = f(s.h), f(s.dt), f(s.box_half_width), f(s.elasticity), f(s.wall_offset)
+    p, v = p.astype(f).copy(), v.astype(f).copy()
+    g3 = (f(0), f(s.g), f(0))
+    for a in range(3):
+        acc = f(f(F[a] / rho) + g3[a])
+        v[a] = f(v[a] + f(acc * dt))
+        p[a] = f(p[a] + f(v[a] * dt))
+    hmb, bmh = f(h - box), f(-h + box)
+    if p[1] < h:
+        p[1] = f(f(-p[1] + f(f(2) * h)) + off)
+        v[1] = f(-v[1] * el)
+    for a in (0, 2):
+        if p[a] < hmb:
+            p[a] = f(f(-p[a] + f(f(2) * hmb)) + off)
+            v[a] = f(-v[a] * el)
+        if p[a] > bmh:
+            p[a] = f(f(-p[a] + f(f(2) * f(-hmb))) - off)
+            v[a] = f(-v[a] * el)
+    return p, v
+
+
 def test_sums_are_taken_in_the_documented_order(sph):
     """Bit-exact check of the summation order itself, against a numpy restatement: for rows of the one-thread
     kernel, for clump rows (tiled phase of the heavy kernel) and for rows that get a warp of their own (deferred,
@@ -310,7 +335,7 @@ def test_sums_are_taken_in_the_documented_order(sph):
     sim = sph.Sim(s, capacity=len(pos))
     sim.upload(pos, vel)
     sim.step(1)
-    out = sim.download(sph.ORDER_ID, fields=("density", "force"))
+    out = sim.download(sph.ORDER_ID, fields=("density", "force", "pos", "vel"))
     got, got_force = out["density"], out["force"]
     st = sim.stats()
     sim.close()
@@ -348,6 +373,10 @@ def test_sums_are_taken_in_the_documented_order(sph):
         # this row; its neighbours' enter as they are)
         fwant = _force_in_documented_order(pos, vel, got, ids_by_cell, i, K)[fclass]
         assert np.array_equal(got_force[i].view(np.uint32), fwant.view(np.uint32)), (i, dclass, fclass, got_force[i], fwant)
+        # ... and from there the integration and the walls: the whole step of this row, bit for bit
+        pw, vw = _integrate_as_the_reference_does(pos[i], vel[i], fwant, got[i], s)
+        assert np.array_equal(out["pos"][i].view(np.uint32), pw.view(np.uint32)), (i, out["pos"][i], pw)
+        assert np.array_equal(out["vel"][i].view(np.uint32), vw.view(np.uint32)), (i, out["vel"][i], vw)
     assert checked["light"] >= 40 and checked["clump"] >= 10 and checked["warp"] >= 5, checked
 
 

@@ -5,7 +5,7 @@ GPU: what the GPU test then proves is the ORDER, on top of physics already prove
 import numpy as np
 
 from conftest import by_id
-from test_gpu_edge import _density_in_documented_order, _force_in_documented_order
+from test_gpu_edge import _density_in_documented_order, _force_in_documented_order, _integrate_as_the_reference_does
 
 
 def test_restated_sums_are_the_reference_physics(oracle):
@@ -28,6 +28,8 @@ def test_restated_sums_are_the_reference_physics(oracle):
     K = dict(h=h, h2=h2, mass=f(s.mass), gas=f(s.gasConstant), rest=f(s.restDensity), visc_mass=f(f(s.viscosity) * f(s.mass)),
              spiky_grad=f(s.spikyGrad), spiky_lap=f(s.spikyLap))
     fmed = float(np.median(np.linalg.norm(want["force"][:1500], axis=1)))
+    class Step:  # the settings the integration needs, under the product's field names
+        h, dt, g, box_half_width, elasticity, wall_offset = s.h, 0.003, s.g, 8.0, 0.5, 0.0001
     checked = 0
     for i in list(rng.choice(1500, 25, replace=False)) + list(1500 + rng.choice(2500, 25, replace=False)):
         c = tuple(cells[i])
@@ -44,5 +46,9 @@ def test_restated_sums_are_the_reference_physics(oracle):
         scale = max(float(np.linalg.norm(fw)), fmed)
         for gotf in forces.values():
             assert float(np.linalg.norm(gotf - fw)) <= 1e-3 * scale, (i, gotf, fw)
+        # integration + walls from the ORACLE's force and density: the restatement must then give the oracle's row
+        pw, vw = _integrate_as_the_reference_does(pos[i], vel[i], fw, want["density"][i], Step)
+        assert np.array_equal(pw.view(np.uint32), want["pos"][i].view(np.uint32)), (i, pw, want["pos"][i])
+        assert np.array_equal(vw.view(np.uint32), want["vel"][i].view(np.uint32)), (i, vw, want["vel"][i])
         checked += 1
     assert checked >= 40
