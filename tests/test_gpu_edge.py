@@ -205,7 +205,25 @@ def test_clump_takes_the_warp_cooperative_kernels(sph, oracle, clump_cell):
         assert_bit_equal(runs[1][0][k], got[k], f"second run: {k}")
 
 
-def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
+_HASH_M = (73856093, 19349663, 83492791)
+
+
+def _hash16(c):
+    return ((c[0] * _HASH_M[0]) ^ (c[1] * _HASH_M[1]) ^ (c[2] * _HASH_M[2])) & 0xFFFF
+
+
+def _bucket_hashes(c):
+    """hash16 of the 27 buckets the reference walks for a particle in cell c (src/sph.cpp:40-44)."""
+    return [_hash16((c[0] + x, c[1] + y, c[2] + z)) for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
+
+
+def _multiplicity(buckets, cj):
+    """How often the reference accepts a neighbour of cell cj: once per bucket with cj's hash (SURVEY.md App. A.3);
+    1 unless two of the 27 bucket hashes collide."""
+    return buckets.count(_hash16(cj)) if len(set(buckets)) < 27 else 1
+
+
+def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens, multiplicities=True):
     """nine runs (x offset outer, z offset inner), each the cells y-1, y, y+1 of a column in
     ascending y, rows of a cell by ascending id. One-thread kernel ("seq"): dens = (float)((double)dens + mp * t^3)
     per accepted row, in that order. Clump rows ("tiled", tiled phase of the heavy kernel): four double-precision
@@ -215,6 +233,7 @@ def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
     longest run and the own cell's size."""
     f = np.float32
     c = tuple(int(v) for v in np.trunc(pos[i] / f(h)).astype(np.int64))
+    buckets = _bucket_hashes(c)
     dens, cnt, longest = f(0), 0, 0
     part = [np.float64(0)] * 4
     lanes = np.zeros(32, np.float64)  # one warp per row: lane (rank in run) % 32, then a butterfly over the lanes
@@ -222,7 +241,9 @@ def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
         for oz in (-1, 0, 1):
             run = 0
             for oy in (-1, 0, 1):
-                for j in ids_by_cell.get((c[0] + ox, c[1] + oy, c[2] + oz), ()):
+                cj = (c[0] + ox, c[1] + oy, c[2] + oz)
+                m = _multiplicity(buckets, cj) if multiplicities else 1
+                for j in ids_by_cell.get(cj, ()):
                     rank = run
                     run += 1
                     if j == i:
@@ -232,10 +253,11 @@ def _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, self_dens):
                     if d2 < h2:
                         t = np.float64(f(h2 - d2))
                         term = np.float64(mp) * ((t * t) * t)
-                        dens = f(np.float64(dens) + term)
-                        part[rank % 4] = part[rank % 4] + term
-                        lanes[rank % 32] = lanes[rank % 32] + term
-                        cnt += 1
+                        for _ in range(m):  # only rows without collisions take the one-thread path: m is 1 there
+                            dens = f(np.float64(dens) + term)
+                        part[rank % 4] = part[rank % 4] + np.float64(m) * term
+                        lanes[rank % 32] = lanes[rank % 32] + np.float64(m) * term
+                        cnt += m
             longest = max(longest, run)
     tiled = f(f((part[0] + part[2]) + (part[1] + part[3])) + self_dens)
     for o in (16, 8, 4, 2, 1):
@@ -252,6 +274,7 @@ def _force_in_documented_order(pos, vel, rho, ids_by_cell, i, K):
     K: dict of float32 constants h, h2, mass, gas, rest, visc_mass, spiky_grad, spiky_lap."""
     f = np.float32
     c = tuple(int(v) for v in np.trunc(pos[i] / K["h"]).astype(np.int64))
+    buckets = _bucket_hashes(c)
     pres_i = f(K["gas"] * f(rho[i] - K["rest"]))
     seq = np.zeros(3, f)
     part = np.zeros((4, 3), f)
@@ -266,7 +289,9 @@ def _force_in_documented_order(pos, vel, rho, ids_by_cell, i, K):
             for oz in (-1, 0, 1):
                 run = 0
                 for oy in (-1, 0, 1):
-                    for j in ids_by_cell.get((c[0] + ox, c[1] + oy, c[2] + oz), ()):
+                    cj = (c[0] + ox, c[1] + oy, c[2] + oz)
+                    m = _multiplicity(buckets, cj)
+                    for j in ids_by_cell.get(cj, ()):
                         rank = run
                         run += 1
                         if j == i:
@@ -289,8 +314,9 @@ def _force_in_documented_order(pos, vel, rho, ids_by_cell, i, K):
                             u = f(vel[j][a] - vel[i][a])
                             V[a] = f(f(f(K["visc_mass"] * f(u / rho[j])) * K["spiky_lap"]) * hd)
                         for acc in (seq, part[rank % 4], lanes[rank % 32]):
-                            add(acc, P)
-                            add(acc, V)
+                            for _ in range(m):  # a neighbour accepted m times adds its two terms m times, back to back
+                                add(acc, P)
+                                add(acc, V)
         tiled = np.array([f(f(part[0][a] + part[2][a]) + f(part[1][a] + part[3][a])) for a in range(3)], f)
         for o in (16, 8, 4, 2, 1):
             lanes = (lanes + lanes[np.arange(32) ^ o]).astype(f)
@@ -325,7 +351,8 @@ def _integrate_as_the_reference_does(p, v, F, rho, s):
 def test_sums_are_taken_in_the_documented_order(sph):
     """Bit-exact check of the summation order itself, against a numpy restatement: for rows of the one-thread
     kernel, for clump rows (tiled phase of the heavy kernel) and for rows that get a warp of their own (deferred,
-    own cell below the clump threshold). Hash-collision neighbourhoods (multiplicities) are skipped."""
+    own cell below the clump threshold), hash-collision neighbourhoods — whose neighbours count once per colliding
+    bucket — included."""
     rng = np.random.default_rng(5)
     s = sph.default_settings()
     d = rng.normal(size=(1500, 3))
@@ -336,32 +363,53 @@ def test_sums_are_taken_in_the_documented_order(sph):
     sim.upload(pos, vel)
     sim.step(1)
     out = sim.download(sph.ORDER_ID, fields=("density", "force", "pos", "vel"))
-    got, got_force = out["density"], out["force"]
     st = sim.stats()
     sim.close()
     assert st.deferred_density >= 1400
     dv = sph.derive(s)
+    checked = {"light": 0, "clump": 0, "warp": 0, "collision": 0}
+    rows = list(rng.choice(1500, 60, replace=False)) + list(1500 + rng.choice(2500, 60, replace=False))
+    _check_rows_bit_for_bit(rows, pos, vel, out, st, s, dv, checked)
+    assert checked["light"] >= 40 and checked["clump"] >= 10 and checked["warp"] >= 5, checked
+
+    # The dense golden cube holds the rows in whose neighbourhood two of the reference's 27 buckets share a hash16:
+    # 16 of them have neighbours that the reference therefore counts twice.
+    from conftest import load_golden
+    g = load_golden("cube20_step200.npz")
+    pos, vel = g["pos0"], g["vel0"]
+    sim = sph.Sim(s, capacity=len(pos))
+    sim.upload(pos, vel)
+    sim.step(1)
+    out = sim.download(sph.ORDER_ID, fields=("density", "force", "pos", "vel"))
+    st = sim.stats()
+    sim.close()
+    cells = np.trunc(pos / np.float32(s.h)).astype(np.int64)
+    collision_rows = [j for j, c in enumerate(map(tuple, cells)) if len(set(_bucket_hashes(c))) < 27]
+    checked = {"light": 0, "clump": 0, "warp": 0, "collision": 0, "counted_twice": 0}
+    _check_rows_bit_for_bit(collision_rows + list(rng.choice(len(pos), 20, replace=False)), pos, vel, out, st, s, dv, checked)
+    assert checked["collision"] >= 60 and checked["counted_twice"] >= 16 and checked["light"] >= 10, checked
+
+
+def _check_rows_bit_for_bit(rows, pos, vel, out, st, s, dv, checked):
+    """Density, force, position and velocity of the given rows after one step from (pos, vel): the GPU's bits (out)
+    against the numpy restatement in the order of the kernel class each row falls into."""
     f = np.float32
     h, h2, mp = f(s.h), f(dv.h2), f(f(s.mass) * f(dv.poly6))
     K = dict(h=h, h2=h2, mass=f(s.mass), gas=f(s.gas_constant), rest=f(s.rest_density), visc_mass=f(f(s.viscosity) * f(s.mass)),
              spiky_grad=f(dv.spiky_grad), spiky_lap=f(dv.spiky_lap))
+    got, got_force = out["density"], out["force"]
     cells = np.trunc(pos / h).astype(np.int64)
     ids_by_cell = {}
     for j, c in enumerate(map(tuple, cells)):
         ids_by_cell.setdefault(c, []).append(j)
-    M = (73856093, 19349663, 83492791)
-
-    def collides(c):
-        hs = [((c[0] + x) * M[0] ^ (c[1] + y) * M[1] ^ (c[2] + z) * M[2]) & 0xFFFF
-              for x in (-1, 0, 1) for y in (-1, 0, 1) for z in (-1, 0, 1)]
-        return len(set(hs)) < 27
-
-    checked = {"light": 0, "clump": 0, "warp": 0}
-    for i in list(rng.choice(1500, 60, replace=False)) + list(1500 + rng.choice(2500, 60, replace=False)):
-        if collides(tuple(cells[i])):
-            continue
+    for i in rows:
         dens, cnt, longest, own = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(dv.self_dens))
-        deferred = longest > 96 or cnt > st.nlist_rows
+        collision = len(set(_bucket_hashes(tuple(cells[i])))) < 27  # such a row may count some neighbours several times
+        checked["collision"] += collision
+        if "counted_twice" in checked:
+            unique = _density_in_documented_order(pos, ids_by_cell, i, h, h2, mp, f(dv.self_dens), multiplicities=False)[1]
+            checked["counted_twice"] += cnt > unique
+        deferred = collision or longest > 96 or cnt > st.nlist_rows
         # which kernel sums this row: the density pass, then the force pass (a deferred row whose list fits is
         # back with the one-thread force kernel, which reads the list the heavy kernel wrote in walk order)
         dclass = "seq" if not deferred else ("tiled" if own >= 64 else "warp")
@@ -377,7 +425,6 @@ def test_sums_are_taken_in_the_documented_order(sph):
         pw, vw = _integrate_as_the_reference_does(pos[i], vel[i], fwant, got[i], s)
         assert np.array_equal(out["pos"][i].view(np.uint32), pw.view(np.uint32)), (i, out["pos"][i], pw)
         assert np.array_equal(out["vel"][i].view(np.uint32), vw.view(np.uint32)), (i, out["vel"][i], vw)
-    assert checked["light"] >= 40 and checked["clump"] >= 10 and checked["warp"] >= 5, checked
 
 
 def test_captured_steps_replay_the_same_bits():
